@@ -1,0 +1,304 @@
+"""CPU-only tests of the host side: tap generation and program packing against the reference
+fixtures, the reference-facing API contracts (names, errors, laziness), and the C ABI surface
+(library loads, every declared symbol is exported, no compute without a GPU)."""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import vnd_oracle as O
+from tests import _golden as G
+from vndecorrelate_b200 import _native as N
+from vndecorrelate_b200 import taps as T
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu() -> bool:
+    n = C.c_int(0)
+    return N.lib().vnd_device_count(C.byref(n)) == 0 and n.value > 0
+
+
+# ------------------------------------------------------------------ tap tables
+
+
+def _table(**kw):
+    base = dict(sample_rate_hz=44100, duration_seconds=0.03, num_impulses=30, num_outs=2, num_segments=4,
+                log_distribution_strength=1.0, filtered_channels=(0, 1), seed=1)
+    base.update(kw)
+    return T.generate_tap_table(**base)
+
+
+def test_tables_match_reference():
+    t = _table()
+    assert np.array_equal(t.rows(), G.tables()["cfg1"])
+    t3 = _table(sample_rate_hz=48000, num_outs=4096, filtered_channels=tuple(range(4096)))
+    assert G.sha(t3.rows()) == G.hashes()["tables"]["cfg3"]["sha256"]
+    t4 = _table(sample_rate_hz=96000, duration_seconds=0.3, num_impulses=300, num_outs=4, filtered_channels=(0, 1, 2, 3))
+    assert G.sha(t4.rows()) == G.hashes()["tables"]["cfg4_4ch"]["sha256"]
+    for k in (0.0, 0.123, 0.5, 1.0):
+        tk = _table(sample_rate_hz=48000, log_distribution_strength=k, filtered_channels=(0,))
+        assert np.array_equal(tk.rows(), G.tables()[f"cand_{k}"])
+        assert tk[1] == []
+
+
+def test_cfg5_candidate_tables_hash():
+    import hashlib
+
+    h = hashlib.sha256()
+    for k in np.linspace(0.0, 1.0, 1024):
+        h.update(_table(sample_rate_hz=48000, log_distribution_strength=k, filtered_channels=(0,)).rows().tobytes())
+    assert h.hexdigest() == G.hashes()["tables"]["cfg5_1024_candidates"]["sha256_concat"]
+
+
+def test_table_is_sliced_not_regenerated_per_shard():
+    """Channel c of a 2-channel generator is NOT channel c of a wider one with the same seed
+    (decorrelation.py:510-520), so shards must slice one table."""
+    narrow = _table()
+    wide = _table(num_outs=4, filtered_channels=(0, 1, 2, 3))
+    assert not np.array_equal(narrow.index[0], wide.index[0])
+    prog = T.segmented_program(wide, O.DEFAULT_ENVELOPE, 10000)
+    part = prog.slice_channels(2, 4)
+    full_rows = wide.rows()
+    assert part.channels == 2 and part.offsets[0] == 0
+    want = T.segmented_program(
+        T.TapTable(wide.fir_length_samples, 30, 4, wide.filtered[2:], wide.index[2:], wide.positive[2:], wide.segment), O.DEFAULT_ENVELOPE, 10000)
+    assert np.array_equal(part.words, want.words) and np.array_equal(part.offsets, want.offsets)
+    assert len(full_rows) == 120
+
+
+def test_filtered_channel_quirk():
+    with pytest.raises(IndexError):
+        _table(filtered_channels=(1,))
+
+
+@pytest.mark.parametrize("name", ["gen_cfg1", "gen_g3", "gen_trunc"])
+def test_generate_velvet_noise(name):
+    meta = G.hashes()["tables"][name]
+    kw = dict(meta["kwargs"])
+    if "segment_envelope" in kw:
+        kw["segment_envelope"] = tuple(kw["segment_envelope"])
+    f = T.generate_dense_fir(**kw)
+    assert list(f.shape) == meta["shape"] and f.dtype == np.float32
+    assert np.array_equal(np.argwhere(f != 0).astype(np.int32), G.tables()[name + "_nz"])
+    assert np.array_equal(f[f != 0], G.tables()[name + "_val"])
+
+
+# ------------------------------------------------------------------ program packing (interpreted on the CPU)
+
+
+def _interpret(prog: T.TapProgram, x: np.ndarray) -> np.ndarray:
+    """Executes a tap program the way the kernels are specified to (include/vnd_b200.h), in numpy,
+    so that the packing can be checked against the oracle without a GPU."""
+    n = len(x)
+    y = np.zeros((n, prog.channels), dtype=np.float32)
+    for c in range(prog.channels):
+        w = prog.words[prog.offsets[c] : prog.offsets[c + 1]]
+        if len(w) == 0:
+            y[:, c] = x[:, c]
+            continue
+        if prog.order == N.ORDER_SEGMENTED:
+            S = int(w[0])
+            tp = 1 + 3 * S
+            for s in range(S):
+                nn, npos, gbits = int(w[1 + 3 * s]), int(w[2 + 3 * s]), w[3 + 3 * s : 4 + 3 * s]
+                acc = np.zeros(n, dtype=np.float32)
+                for i in w[tp : tp + nn]:
+                    acc[: n - i] -= x[i:, c]
+                tp += nn
+                for i in w[tp : tp + npos]:
+                    acc[: n - i] += x[i:, c]
+                tp += npos
+                if prog.apply_gain:
+                    acc *= gbits.view(np.float32)[0]
+                y[:, c] += acc
+        else:
+            K = int(w[0])
+            for k in range(K):
+                i = int(w[1 + 3 * k])
+                coef = np.array([w[2 + 3 * k], w[3 + 3 * k]], dtype=np.int32).view(np.float64)[0]
+                v = np.float32(coef) if prog.order == N.ORDER_ASCENDING else coef
+                y[: n - i, c] += x[i:, c] * v
+    return y
+
+
+@pytest.mark.parametrize("c", G.case_list("vn_convolve"), ids=lambda c: f"case{c['id']}")
+def test_segmented_program_semantics(c):
+    x, y = G.case_xy(c)
+    p = c["params"]
+    t = _table(num_outs=p["num_outs"], filtered_channels=tuple(p["filtered_channels"]), seed=p["seed"])
+    prog = T.segmented_program(t, O.DEFAULT_ENVELOPE, len(x))
+    assert prog.halo <= len(x) and prog.channels == p["num_outs"]
+    assert G.same_bits(_interpret(prog, x), y)
+
+
+@pytest.mark.parametrize("c", G.case_list("fn_convolve"), ids=lambda c: f"case{c['id']}")
+def test_ascending_program_semantics(c):
+    x, y = G.case_xy(c)
+    fir = G.cases()[1][c["params"]["fir"]]
+    prog = T.ascending_program(fir, len(x))
+    assert prog.order == (N.ORDER_ASCENDING if fir.dtype == np.float32 else N.ORDER_ASCENDING_F64)
+    assert G.same_bits(_interpret(prog, x), y)
+
+
+def test_program_drops_empty_segments_and_long_taps():
+    t = _table(duration_seconds=0.5, num_impulses=15)  # 22 050-sample filter
+    prog = T.segmented_program(t, O.DEFAULT_ENVELOPE, 1000)
+    assert prog.halo <= 1000
+    w = prog.words[: prog.offsets[1]]
+    S = int(w[0])
+    assert S < 4 and all(int(w[1 + 3 * s]) + int(w[2 + 3 * s]) > 0 for s in range(S))
+    ident = T.segmented_program(t, (1.0,), 30000)
+    assert ident.apply_gain == 0
+    one = _table(duration_seconds=0.5, num_impulses=15, num_segments=1)
+    lst = T.segmented_program(one, [1.0], 30000)  # a list is not the identity tuple: multiplied by 1.0
+    assert lst.apply_gain == 1
+    with pytest.raises(IndexError):
+        T.segmented_program(t, (0.5, 0.25), 30000)
+
+
+def test_candidate_program_layout():
+    tables = [_table(sample_rate_hz=48000, log_distribution_strength=k, filtered_channels=(0,)) for k in (0.0, 0.5, 1.0)]
+    prog = T.candidate_program(tables, O.DEFAULT_ENVELOPE, 48000)
+    assert prog.channels == 3 and prog.offsets[-1] == prog.words.size
+    for i, t in enumerate(tables):
+        one = T.segmented_program(T.TapTable(t.fir_length_samples, 30, 4, t.filtered[:1], t.index[:1], t.positive[:1], t.segment), O.DEFAULT_ENVELOPE, 48000)
+        assert np.array_equal(prog.words[prog.offsets[i] : prog.offsets[i + 1]], one.words)
+
+
+# ------------------------------------------------------------------ reference-facing API contracts (no device needed)
+
+
+def test_velvet_noise_contracts():
+    from vndecorrelate_b200.decorrelation import VelvetNoise
+
+    vn = VelvetNoise(sample_rate_hz=44100, seed=1)
+    assert vn._generate() == vn._velvet_noise  # tests/test_decorrelation.py:56-68
+    assert VelvetNoise(sample_rate_hz=44100, seed=2)._velvet_noise != vn._velvet_noise
+    assert VelvetNoise(sample_rate_hz=44100, log_distribution_strength=0.0, seed=1)._velvet_noise != vn._velvet_noise
+    before = vn._velvet_noise
+    _ = vn.FIR
+    assert vn.velvet_noise is before  # generated once, tests/test_decorrelation.py:161-169
+    assert VelvetNoise(duration_seconds=0.03, num_impulses=30, sample_rate_hz=44100).density == 1000
+    v = VelvetNoise(sample_rate_hz=44100, duration_seconds=0.055, num_impulses=45, seed=6)
+    assert 818.19 > v.density > 818.18
+    assert v.FIR.shape == (2426, 2) and np.count_nonzero(v.FIR[:, 0]) == 45
+    assert G.same_bits(v.FIR, G.tables()["fir_prop_055_45_seed6"])
+    with pytest.raises(ValueError):
+        VelvetNoise(duration_seconds=0.03, num_impulses=700, sample_rate_hz=44100)
+    vn.num_impulses = 20  # triggers regeneration on next access (decorrelation.py:368-379)
+    assert vn.velvet_noise.num_impulses == 20
+    assert VelvetNoise(sample_rate_hz=44100, segment_envelope=()).segment_envelope == (1.0,)
+    with pytest.raises(ValueError):  # MS mode needs a stereo pair (utils/dsp.py:57-58)
+        VelvetNoise(sample_rate_hz=44100, num_outs=4, filtered_channels=(0, 1, 2, 3)).decorrelate(np.zeros((10, 4), np.float32))
+
+
+def test_signal_chain_contracts():
+    from vndecorrelate_b200.decorrelation import HaasEffect, SignalChain, VelvetNoise, _fusable
+
+    with pytest.raises(TypeError):
+        SignalChain(sample_rate_hz=44100, _decorrelators=[])
+    with pytest.raises(TypeError):
+        SignalChain(sample_rate_hz=44100).velvet_noise(sample_rate_hz=48000)
+    chain = SignalChain(sample_rate_hz=44100).velvet_noise(seed=1).haas_effect(delay_time_seconds=0.02)
+    assert all(callable(d) and not isinstance(d, (VelvetNoise, HaasEffect)) for d in chain._decorrelators)  # lazy
+    chain._init_decorrelators()
+    assert isinstance(chain._decorrelators[0], VelvetNoise) and isinstance(chain._decorrelators[1], HaasEffect)
+    assert _fusable(*chain._decorrelators)
+    assert not _fusable(chain._decorrelators[0], HaasEffect(sample_rate_hz=44100, mode="MS"))
+    assert not _fusable(chain._decorrelators[0], HaasEffect(sample_rate_hz=44100, width=0.5))
+    hot = SignalChain(sample_rate_hz=44100, lazy=False).velvet_noise(seed=1)
+    assert isinstance(hot._decorrelators[0], VelvetNoise)
+    bad = SignalChain(sample_rate_hz=44100).velvet_noise(num_outs=2)  # error surfaces at first call, as in the reference
+    with pytest.raises(TypeError):
+        bad(np.zeros(10))
+    with pytest.raises(NotImplementedError):
+        SignalChain(sample_rate_hz=44100).white_noise(duration_seconds=0.03)
+    assert HaasEffect(sample_rate_hz=44100, delay_time_seconds=0.02).delay_len_samples == 882
+
+
+def test_function_path_contracts():
+    from vndecorrelate_b200.decorrelation import convolve_velvet_noise, generate_velvet_noise
+
+    fir = generate_velvet_noise(duration_seconds=0.03, num_impulses=30, seed=1)
+    assert fir.shape == (1323, 2) and fir.dtype == np.float32
+    with pytest.raises(IndexError):  # 1-D input, decorrelation.py:650
+        convolve_velvet_noise(np.zeros(100, np.float32), fir)
+    with pytest.raises(ValueError):  # channel mismatch, utils/dsp.py:305-310
+        convolve_velvet_noise(np.zeros((100, 3), np.float32), fir)
+
+
+def test_local_minima_rule():
+    from vndecorrelate_b200.optimization import get_local_minima
+
+    assert get_local_minima(np.array([3.0, 1.0, 2.0, 0.5, 4.0]), 5) == [1, 3]
+    assert get_local_minima(np.array([0.0, 1.0, 2.0, 3.0]), 4) == [0]  # no interior minimum -> argmin
+    assert get_local_minima(np.array([1.0, 1.0, 1.0]), 3) == [0]  # strict comparisons
+
+
+def test_score_combination_matches_reference_dtype_chain():
+    """The scalar combination applied to partial sums computed from the reference's own terms
+    reproduces the reference's float32 score (viola)."""
+    from vndecorrelate_b200.optimization import _vn_score
+
+    for row in G.objective()["viola_vn"]:
+        p = np.zeros(12)
+        p[0] = row["sum_r"]
+        p[1], p[2], p[3] = row["centroid"] * row["sum_r"], row["spread"] * row["sum_r"], row["m3"] * row["sum_r"]
+        p[4], p[5] = row["dot_lr"], row["norm_l"] ** 2
+        p[6], p[7] = np.tan(np.float64(row["max_abs_theta"])), 1.0  # a frame whose angle is the recorded maximum
+        p[8], p[9] = 0.0, 1.0
+        got = _vn_score(p, angle_limit=np.pi / 4, lambda_mean=5.0, lambda_skew=2.0, lambda_correlation=15.0, lambda_penalty=1e3)
+        assert isinstance(got, np.float32)
+        assert abs(float(got) - row["objective"]) <= 2e-4
+
+
+# ------------------------------------------------------------------ C ABI surface
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "vnd_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vnd_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared_functions()
+    assert len(names) >= 25
+    lib = N.lib()
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/vnd_b200.h but not exported"
+    assert set(names) == set(N.SIGNATURES), set(names) ^ set(N.SIGNATURES)
+    assert lib.vnd_abi_version() == 1
+    assert b"sm_100a" in lib.vnd_version()
+    assert lib.vnd_status_string(N.VND_EPROGRAM) == b"malformed tap program"
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(N.SignalStruct) == 40
+    assert C.sizeof(N.TapProgramStruct) == 48
+    assert C.sizeof(N.EpilogueStruct) == 32
+
+
+def test_argument_errors_do_not_need_a_device():
+    lib = N.lib()
+    n = C.c_size_t()
+    assert lib.vnd_vn_decorrelate_workspace(-1, 2, C.byref(N.EpilogueStruct()), C.byref(n)) == N.VND_EINVAL
+    assert b"negative" in lib.vnd_last_error()
+    assert lib.vnd_ctx_create(0, None) == N.VND_EINVAL
+
+
+@pytest.mark.skipif(_has_gpu(), reason="this checks the behaviour WITHOUT a device")
+def test_no_gpu_means_loud_failure_not_fallback():
+    from vndecorrelate_b200.decorrelation import VelvetNoise
+
+    h = C.c_void_p()
+    assert N.lib().vnd_ctx_create(0, C.byref(h)) == N.VND_ECUDA
+    assert b"no CPU fallback" in N.lib().vnd_last_error()
+    with pytest.raises(N.VndError):
+        VelvetNoise(sample_rate_hz=44100, seed=1).decorrelate(np.zeros((100, 2), np.float32))

@@ -1,0 +1,413 @@
+// Post-FIR kernels: numpy-order sum of squares, RMS gains, gain + Haas placement, the standalone
+// Haas delay and the in-place stereo helpers.
+//
+// Reference arithmetic reproduced here:
+//   rms_normalize                src/vndecorrelate/utils/dsp.py:87-109
+//   HaasEffect.haas_delay        src/vndecorrelate/decorrelation.py:202-230
+//   LR_to_MS / MS_to_LR          src/vndecorrelate/utils/dsp.py:124-167
+//   apply_stereo_width           src/vndecorrelate/utils/dsp.py:21-37
+//   encode_signal_to_side_channel src/vndecorrelate/utils/dsp.py:40-63
+
+#include "vnd_common.cuh"
+
+namespace vnd {
+
+// ------------------------------------------------------------------------------------------------
+// np.mean(np.square(a), axis=0) on a C-order (n, C) array adds row after row into one accumulator
+// per column: a strict left-to-right running sum in the array's dtype.  That order loses low bits
+// on long signals, and the reference's gains inherit the loss, so it is reproduced: one CTA per
+// column, warps 1.. stage the rounded squares of the next chunk in shared memory while lane 0 of
+// warp 0 walks the current chunk with a dependent add chain (4 cycles per sample).
+// ------------------------------------------------------------------------------------------------
+struct SeqParams {
+  const void* a;
+  long long a_st, a_sc;
+  const void* b;  // optional second signal (columns C .. 2C-1)
+  long long b_st, b_sc;
+  long long frames;
+  int channels;
+  void* sums;  // T[ncols]
+};
+
+template <typename T>
+__device__ __forceinline__ T sq(T v);
+template <>
+__device__ __forceinline__ float sq<float>(float v) { return fmul(v, v); }
+template <>
+__device__ __forceinline__ double sq<double>(double v) { return dmul(v, v); }
+template <typename T>
+__device__ __forceinline__ T add_rn(T a, T b);
+template <>
+__device__ __forceinline__ float add_rn<float>(float a, float b) { return fadd(a, b); }
+template <>
+__device__ __forceinline__ double add_rn<double>(double a, double b) { return dadd(a, b); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) seq_sumsq_kernel(const SeqParams p) {
+  constexpr int CHUNK = 16384 / (int)sizeof(T);  // 2 x 16 KB of static shared memory
+  constexpr int NT = 256;
+  __shared__ __align__(16) T buf[2][CHUNK];
+  const int col = blockIdx.x;
+  const T* base;
+  long long st;
+  if (col < p.channels) {
+    base = reinterpret_cast<const T*>(p.a) + (long long)col * p.a_sc;
+    st = p.a_st;
+  } else {
+    base = reinterpret_cast<const T*>(p.b) + (long long)(col - p.channels) * p.b_sc;
+    st = p.b_st;
+  }
+  const int tid = threadIdx.x;
+  const long long nchunks = ceil_div<long long>(p.frames, CHUNK);
+  auto stage = [&](long long k, int slot, int first, int step) {
+    const long long off = k * CHUNK;
+    for (int i = first; i < CHUNK; i += step) {
+      const long long t = off + i;
+      buf[slot][i] = t < p.frames ? sq<T>(base[t * st]) : (T)0;  // +0 padding: s + 0 == s
+    }
+  };
+  if (nchunks > 0) stage(0, 0, tid, NT);
+  T s = (T)0;
+  for (long long k = 0; k < nchunks; ++k) {
+    __syncthreads();
+    if (tid < 32) {
+      if (tid == 0) {
+        const T* q = buf[k & 1];
+        const long long left = p.frames - k * CHUNK;
+        const int n = (int)(left < CHUNK ? left : CHUNK);
+        const int n8 = (n + 7) & ~7;
+#pragma unroll 2
+        for (int i = 0; i < n8; i += 8) {
+          T v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = q[i + j];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s = add_rn<T>(s, v[j]);
+        }
+      }
+    } else if (k + 1 < nchunks) {
+      stage(k + 1, (int)((k + 1) & 1), tid - 32, NT - 32);
+    }
+  }
+  if (tid == 0) reinterpret_cast<T*>(p.sums)[col] = s;
+}
+
+// gains[c] = sqrt(mean_x[c]) / sqrt(mean_y[c] + eps) with numpy's dtype chain: the mean divides in
+// float64 (np.mean's true_divide by an intp count) and stores the array dtype; eps is a weak
+// Python float, i.e. it is cast to the array dtype.  sums = [x columns..., y columns...].
+template <typename T>
+__global__ void rms_gain_kernel(const T* __restrict__ sums, T* __restrict__ gains, int channels, long long frames) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= channels) return;
+  if constexpr (sizeof(T) == 4) {
+    const float mx = __double2float_rn((double)sums[c] / (double)frames);
+    const float my = __double2float_rn((double)sums[channels + c] / (double)frames);
+    gains[c] = __fdiv_rn(__fsqrt_rn(mx), __fsqrt_rn(fadd(my, 1e-10f)));
+  } else {
+    const double mx = __ddiv_rn(sums[c], (double)frames);
+    const double my = __ddiv_rn(sums[channels + c], (double)frames);
+    gains[c] = __ddiv_rn(__dsqrt_rn(mx), __dsqrt_rn(dadd(my, 1e-10)));
+  }
+}
+
+// out[m, c] = y[m - shift_c, c] * gain[c] (0 outside), shift_c = delay for the delayed channel.
+struct PlaceParams {
+  const float* y;
+  long long y_st, y_sc;
+  void* out;
+  long long o_st, o_sc;
+  long long frames;  // of y
+  int channels;
+  const float* gains;  // nullable
+  int delay, delay_ch;
+};
+
+template <typename TOut>
+__global__ void __launch_bounds__(256) place_kernel(const PlaceParams p) {
+  const long long total = (p.frames + p.delay) * p.channels;
+  TOut* __restrict__ out = reinterpret_cast<TOut*>(p.out);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long m = e / p.channels;
+    const int c = (int)(e - m * p.channels);
+    const long long n = m - (c == p.delay_ch ? p.delay : 0);
+    float v = 0.0f;
+    if (n >= 0 && n < p.frames) {
+      v = p.y[n * p.y_st + c * p.y_sc];
+      if (p.gains) v = fmul(v, p.gains[c]);
+    }
+    out[m * p.o_st + c * p.o_sc] = (TOut)v;
+  }
+}
+
+// HaasEffect.decorrelate in closed form (float64 throughout).
+struct HaasParams {
+  const float* x;
+  long long x_st, x_sc;
+  double* out;
+  long long o_st, o_sc;
+  long long frames;
+  int delay, delay_ch;
+  int mode_ms, mono, use_width;
+  double width;
+};
+
+__global__ void __launch_bounds__(256) haas_kernel(const HaasParams p) {
+  const long long total = p.frames + p.delay;
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < total; m += (long long)gridDim.x * blockDim.x) {
+    // channel pair (as the reference stores it after the optional LR->MS) at frame q, 0 outside
+    auto chan = [&](long long q, int c) -> double {
+      if (q < 0 || q >= p.frames) return 0.0;
+      const double a = (double)p.x[q * p.x_st];
+      const double b = (double)p.x[q * p.x_st + p.x_sc];
+      if (p.mode_ms && !p.mono) return c == 0 ? dmul(dadd(a, b), 0.5) : dmul(dsub(a, b), 0.5);
+      return c == 0 ? a : b;
+    };
+    double c0 = chan(m - (p.delay_ch == 0 ? p.delay : 0), 0);
+    double c1 = chan(m - (p.delay_ch == 1 ? p.delay : 0), 1);
+    if (p.mode_ms) {
+      const double l = dadd(c0, c1), r = dsub(c0, c1);
+      c0 = l;
+      c1 = r;
+      if (p.mono) {
+        c0 = dmul(c0, 0.5);
+        c1 = dmul(c1, 0.5);
+      }
+    }
+    if (p.use_width) {
+      double M = dmul(dadd(c0, c1), 0.5);
+      double S = dmul(dsub(c0, c1), 0.5);
+      M = dmul(M, dsub(1.0, p.width));
+      S = dmul(S, p.width);
+      c0 = dadd(M, S);
+      c1 = dsub(M, S);
+    }
+    p.out[m * p.o_st] = c0;
+    p.out[m * p.o_st + p.o_sc] = c1;
+  }
+}
+
+// In-place helpers on a (frames, 2) signal.
+struct StereoOpParams {
+  void* a;
+  long long a_st, a_sc;
+  const void* dry;
+  long long d_st, d_sc;
+  long long frames;
+  int op;
+  double width;
+  const void* gains;
+};
+
+template <typename T>
+__device__ __forceinline__ T t_add(T a, T b) { return a + b; }
+template <>
+__device__ __forceinline__ float t_add<float>(float a, float b) { return fadd(a, b); }
+template <>
+__device__ __forceinline__ double t_add<double>(double a, double b) { return dadd(a, b); }
+template <typename T>
+__device__ __forceinline__ T t_sub(T a, T b);
+template <>
+__device__ __forceinline__ float t_sub<float>(float a, float b) { return fsub(a, b); }
+template <>
+__device__ __forceinline__ double t_sub<double>(double a, double b) { return dsub(a, b); }
+template <typename T>
+__device__ __forceinline__ T t_mul(T a, T b);
+template <>
+__device__ __forceinline__ float t_mul<float>(float a, float b) { return fmul(a, b); }
+template <>
+__device__ __forceinline__ double t_mul<double>(double a, double b) { return dmul(a, b); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) stereo_op_kernel(const StereoOpParams p) {
+  T* a = reinterpret_cast<T*>(p.a);
+  const T* dry = reinterpret_cast<const T*>(p.dry);
+  const T half = (T)0.5;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < p.frames; t += (long long)gridDim.x * blockDim.x) {
+    T u = a[t * p.a_st], v = a[t * p.a_st + p.a_sc];
+    switch (p.op) {
+      case 0: {  // LR_to_MS
+        const T M = t_mul<T>(t_add<T>(u, v), half), S = t_mul<T>(t_sub<T>(u, v), half);
+        u = M;
+        v = S;
+      } break;
+      case 1: {  // MS_to_LR
+        const T L = t_add<T>(u, v), R = t_sub<T>(u, v);
+        u = L;
+        v = R;
+      } break;
+      case 2: {  // apply_stereo_width
+        T M = t_mul<T>(t_add<T>(u, v), half), S = t_mul<T>(t_sub<T>(u, v), half);
+        M = t_mul<T>(M, (T)(1.0 - p.width));
+        S = t_mul<T>(S, (T)p.width);
+        u = t_add<T>(M, S);
+        v = t_sub<T>(M, S);
+      } break;
+      case 3: {  // encode_signal_to_side_channel
+        const T M = t_add<T>(dry[t * p.d_st], dry[t * p.d_st + p.d_sc]);
+        const T S = t_mul<T>(t_sub<T>(u, v), half);
+        u = t_mul<T>(t_add<T>(M, S), half);
+        v = t_mul<T>(t_sub<T>(M, S), half);
+      } break;
+      default: {  // 4: scale by per-channel gains
+        const T* g = reinterpret_cast<const T*>(p.gains);
+        u = t_mul<T>(u, g[0]);
+        v = t_mul<T>(v, g[1]);
+      } break;
+    }
+    a[t * p.a_st] = u;
+    a[t * p.a_st + p.a_sc] = v;
+  }
+}
+
+// In-place per-channel scale of a (frames, C) float32 signal.
+__global__ void __launch_bounds__(256) scale_kernel(float* y, long long y_st, long long y_sc, long long frames, int channels,
+                                                    const float* __restrict__ gains) {
+  const long long total = frames * channels;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long t = e / channels;
+    const int c = (int)(e - t * channels);
+    float* q = y + t * y_st + c * y_sc;
+    *q = fmul(*q, gains[c]);
+  }
+}
+
+
+// (rows, cols) row-major -> (cols, rows) row-major through a padded shared-memory tile, so that both
+// the loads and the stores are coalesced.  Used to turn wide frame-interleaved slabs into planar
+// ones (and back) around the planar FIR kernel.
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, long long rows,
+                                                        long long cols) {
+  __shared__ float tile[32][33];
+  const long long tiles_c = ceil_div<long long>(cols, 32);
+  const long long tr = blockIdx.x / tiles_c, tc = blockIdx.x % tiles_c;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const long long r = tr * 32 + j, c = tc * 32 + tx;
+    if (r < rows && c < cols) tile[j][tx] = src[r * cols + c];
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const long long c = tc * 32 + j, r = tr * 32 + tx;
+    if (r < rows && c < cols) dst[c * rows + r] = tile[tx][j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+static unsigned grid_for(long long n, int per_block = 256) {
+  DeviceInfo di;
+  if (device_info(&di)) di.sm_count = 148;
+  long long b = ceil_div<long long>(n, per_block);
+  const long long cap = (long long)di.sm_count * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+int seq_sumsq_launch(const vnd_signal* a, const vnd_signal* b, void* sums, cudaStream_t st) {
+  SeqParams p{};
+  p.a = a->data;
+  p.a_st = a->stride_t;
+  p.a_sc = a->stride_c;
+  p.frames = a->frames;
+  p.channels = a->channels;
+  p.sums = sums;
+  int cols = a->channels;
+  if (b) {
+    p.b = b->data;
+    p.b_st = b->stride_t;
+    p.b_sc = b->stride_c;
+    cols *= 2;
+  }
+  if (cols == 0) return VND_OK;
+  if (a->dtype == VND_F64) seq_sumsq_kernel<double><<<cols, 256, 0, st>>>(p);
+  else seq_sumsq_kernel<float><<<cols, 256, 0, st>>>(p);
+  return after_launch("seq_sumsq_kernel");
+}
+
+int rms_gain_launch(const void* sums, void* gains, int channels, long long frames, int dtype, cudaStream_t st) {
+  if (channels == 0) return VND_OK;
+  const unsigned blocks = (unsigned)ceil_div(channels, 128);
+  if (dtype == VND_F64) rms_gain_kernel<double><<<blocks, 128, 0, st>>>((const double*)sums, (double*)gains, channels, frames);
+  else rms_gain_kernel<float><<<blocks, 128, 0, st>>>((const float*)sums, (float*)gains, channels, frames);
+  return after_launch("rms_gain_kernel");
+}
+
+int place_launch(const float* y, long long y_st, long long y_sc, long long frames, int channels, const vnd_signal* out,
+                 const float* gains, int delay, int delay_ch, cudaStream_t st) {
+  PlaceParams p{};
+  p.y = y;
+  p.y_st = y_st;
+  p.y_sc = y_sc;
+  p.out = out->data;
+  p.o_st = out->stride_t;
+  p.o_sc = out->stride_c;
+  p.frames = frames;
+  p.channels = channels;
+  p.gains = gains;
+  p.delay = delay;
+  p.delay_ch = delay_ch;
+  const long long total = (frames + delay) * channels;
+  if (total == 0) return VND_OK;
+  if (out->dtype == VND_F64) place_kernel<double><<<grid_for(total), 256, 0, st>>>(p);
+  else place_kernel<float><<<grid_for(total), 256, 0, st>>>(p);
+  return after_launch("place_kernel");
+}
+
+int scale_launch(float* y, long long y_st, long long y_sc, long long frames, int channels, const float* gains, cudaStream_t st) {
+  if (frames * channels == 0) return VND_OK;
+  scale_kernel<<<grid_for(frames * channels), 256, 0, st>>>(y, y_st, y_sc, frames, channels, gains);
+  return after_launch("scale_kernel");
+}
+
+int haas_launch(const vnd_signal* x, const vnd_signal* out, int delay, int delay_ch, int mode_ms, int mono, int use_width,
+                double width, cudaStream_t st) {
+  HaasParams p{};
+  p.x = reinterpret_cast<const float*>(x->data);
+  p.x_st = x->stride_t;
+  p.x_sc = x->stride_c;
+  p.out = reinterpret_cast<double*>(out->data);
+  p.o_st = out->stride_t;
+  p.o_sc = out->stride_c;
+  p.frames = x->frames;
+  p.delay = delay;
+  p.delay_ch = delay_ch;
+  p.mode_ms = mode_ms;
+  p.mono = mono;
+  p.use_width = use_width;
+  p.width = width;
+  if (p.frames + delay == 0) return VND_OK;
+  haas_kernel<<<grid_for(p.frames + delay), 256, 0, st>>>(p);
+  return after_launch("haas_kernel");
+}
+
+int transpose_launch(const float* src, float* dst, long long rows, long long cols, cudaStream_t st) {
+  if (rows * cols == 0) return VND_OK;
+  const long long blocks = ceil_div<long long>(rows, 32) * ceil_div<long long>(cols, 32);
+  VND_REQUIRE(blocks < 0x7fffffffLL, VND_EUNSUPPORTED, "transpose grid too large");
+  transpose_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, rows, cols);
+  return after_launch("transpose_kernel");
+}
+
+int stereo_op_launch(const vnd_signal* a, const vnd_signal* dry, int op, double width, const void* gains, cudaStream_t st) {
+  StereoOpParams p{};
+  p.a = a->data;
+  p.a_st = a->stride_t;
+  p.a_sc = a->stride_c;
+  if (dry) {
+    p.dry = dry->data;
+    p.d_st = dry->stride_t;
+    p.d_sc = dry->stride_c;
+  }
+  p.frames = a->frames;
+  p.op = op;
+  p.width = width;
+  p.gains = gains;
+  if (p.frames == 0) return VND_OK;
+  if (a->dtype == VND_F64) stereo_op_kernel<double><<<grid_for(p.frames), 256, 0, st>>>(p);
+  else stereo_op_kernel<float><<<grid_for(p.frames), 256, 0, st>>>(p);
+  return after_launch("stereo_op_kernel");
+}
+
+}  // namespace vnd

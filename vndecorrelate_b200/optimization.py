@@ -1,0 +1,321 @@
+"""Stereo-image objective and parameter sweeps with the reference's API
+(``src/vndecorrelate/optimization.py``), evaluated by batched CUDA kernels.
+
+``grid_scan`` recognises the two candidate families the reference's optimisers build —
+``VelvetNoise(filtered_channels=(0,), mode='LR', normalizer=None, log_distribution_strength=k)``
+(optimization.py:260-272) and ``HaasEffect(delay_time_seconds=t, mode='LR')`` (:183-190) — and
+scores ALL candidates of a family in one kernel launch: the clip is read once per tile and every
+candidate is evaluated from shared memory.  Any other decorrelator is run and its output scored by
+the same kernels (one candidate).  The kernels return the sums the objective is made of; the scalar
+combination below follows the reference's dtype chain (float32 for velvet-noise candidates, float64
+for Haas candidates).
+
+Brent refinement stays scipy's ``minimize_scalar`` on the host, as in the reference; each of its
+evaluations is one single-candidate kernel call.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Callable, Sequence
+
+import numpy as np
+
+from . import _native as N
+from . import runtime as R
+from .decorrelation import Decorrelator, HaasEffect, VelvetNoise, _is_mode
+from .taps import IDENTITY_ENVELOPE, TapProgram, candidate_program
+from .utils.dsp import EPSILON, LayoutMode
+
+__all__ = [
+    "symmetry_aware_objective", "grid_scan", "get_local_minima", "optimize_local_minima", "optimize_haas_delay",
+    "optimize_velvet_noise", "vn_objective_partials", "haas_objective_partials", "vn_scores_from_partials", "haas_scores_from_partials",
+]
+
+_F32_HALF_PI = np.float32(np.pi / 2)
+_F32_PI = np.float32(np.pi)
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel calls
+# ------------------------------------------------------------------------------------------------
+
+
+def _planar_clips(clips, dtype=np.float32):
+    """``(n_clips, 2, frames)`` contiguous array from a ``(frames, 2)`` signal, a list of such, or an
+    already planar 3-D array."""
+    if isinstance(clips, np.ndarray) and clips.ndim == 3:
+        return np.ascontiguousarray(clips, dtype=dtype)
+    if isinstance(clips, np.ndarray) and clips.ndim == 2:
+        clips = [clips]
+    if isinstance(clips, np.ndarray) and clips.ndim == 1:
+        clips = [np.column_stack((clips, clips))]
+    frames = clips[0].shape[0]
+    out = np.empty((len(clips), 2, frames), dtype=dtype)
+    for i, c in enumerate(clips):
+        c = np.asarray(c)
+        if c.ndim == 1:
+            c = np.column_stack((c, c))
+        if c.shape != (frames, 2):
+            raise ValueError(f"all clips must be (frames, 2) with the same length, got {c.shape}")
+        out[i] = c.T
+    return out
+
+
+def vn_objective_partials(clips, program: TapProgram):
+    """Per (clip, candidate) partial sums of the objective for velvet-noise candidates.
+
+    ``clips``: float32 ``(n_clips, 2, frames)`` numpy array or CUDA tensor (planar stereo).
+    Returns float64 ``(n_clips, n_candidates, 12)`` (layout in ``include/vnd_b200.h``)."""
+    lib = N.lib()
+    if R.is_torch_tensor(clips):
+        import torch
+
+        if not clips.is_cuda or clips.dtype != torch.float32 or clips.dim() != 3 or clips.shape[1] != 2:
+            raise ValueError("clips must be a CUDA float32 tensor of shape (n_clips, 2, frames)")
+        clips = clips.contiguous()
+        n_clips, _, frames = clips.shape
+        out = torch.empty((n_clips, program.channels, N.OBJ_SLOTS), dtype=torch.float64, device=clips.device)
+        nbytes = C.c_size_t()
+        with torch.cuda.device(clips.device):
+            N.check(lib.vnd_objective_workspace(frames, n_clips, program.channels, C.byref(nbytes)), "vnd_objective_workspace")
+            work = torch.empty(nbytes.value, dtype=torch.uint8, device=clips.device)
+            ps = R.device_program(program, clips.device)
+            N.check(lib.vnd_vn_objective_batch_dev(clips.data_ptr(), frames, n_clips, 2 * frames, frames, C.byref(ps), out.data_ptr(),
+                                                   work.data_ptr(), nbytes.value, R.torch_stream_ptr(clips)), "vnd_vn_objective_batch_dev")
+        return out
+    clips = _planar_clips(clips)
+    n_clips, _, frames = clips.shape
+    out = np.empty((n_clips, program.channels, N.OBJ_SLOTS), dtype=np.float64)
+    ps = program.host_struct()
+    N.check(lib.vnd_vn_objective_batch_host(R.HostContext.get().handle, clips.ctypes.data, frames, n_clips, 2 * frames, frames, C.byref(ps),
+                                            out.ctypes.data), "vnd_vn_objective_batch_host")
+    return out
+
+
+def haas_objective_partials(clips, delays: Sequence[int]):
+    """Per (clip, delay) partial sums for LR Haas candidates delaying channel 0 (float64
+    arithmetic).  ``clips``: float32 or float64 ``(n_clips, 2, frames)``.  Returns float64
+    ``(n_clips, n_delays, 8)``."""
+    lib = N.lib()
+    delays = np.ascontiguousarray(delays, dtype=np.int32)
+    if R.is_torch_tensor(clips):
+        import torch
+
+        if not clips.is_cuda or clips.dtype not in (torch.float32, torch.float64) or clips.dim() != 3 or clips.shape[1] != 2:
+            raise ValueError("clips must be a CUDA float32/float64 tensor of shape (n_clips, 2, frames)")
+        clips = clips.contiguous()
+        n_clips, _, frames = clips.shape
+        out = torch.empty((n_clips, len(delays), N.HAAS_SLOTS), dtype=torch.float64, device=clips.device)
+        with torch.cuda.device(clips.device):
+            d = torch.from_numpy(delays).to(clips.device)
+            N.check(lib.vnd_haas_objective_batch_dev(clips.data_ptr(), N.VND_F64 if clips.dtype == torch.float64 else N.VND_F32, frames, n_clips,
+                                                     2 * frames, frames, d.data_ptr(), len(delays), out.data_ptr(), None, 0,
+                                                     R.torch_stream_ptr(clips)), "vnd_haas_objective_batch_dev")
+        return out
+    dt = np.float64 if (isinstance(clips, np.ndarray) and clips.dtype == np.float64) else np.float32
+    clips = _planar_clips(clips, dt)
+    n_clips, _, frames = clips.shape
+    out = np.empty((n_clips, len(delays), N.HAAS_SLOTS), dtype=np.float64)
+    N.check(lib.vnd_haas_objective_batch_host(R.HostContext.get().handle, clips.ctypes.data, N.VND_F64 if dt == np.float64 else N.VND_F32, frames,
+                                              n_clips, 2 * frames, frames, delays.ctypes.data, len(delays), out.ctypes.data),
+            "vnd_haas_objective_batch_host")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# scalar combination (optimization.py:71-105 and the helpers :11-43)
+# ------------------------------------------------------------------------------------------------
+
+
+def _max_abs_theta_f32(p: np.ndarray) -> np.float32:
+    """max|theta| exactly as the reference's float32 pipeline rounds it, from the two tracked
+    frames: a correctly rounded float32 arctan2 (via float64), then the fold of
+    utils/dsp.py:405-410 in float32."""
+    d_pos, s_pos, d_neg, s_neg = p[6], p[7], p[8], p[9]
+    a = np.float32(np.arctan2(np.float64(d_pos), np.float64(s_pos)))
+    best = a
+    if d_neg > 0.0 or s_neg != 1.0:  # a frame with s < 0 was seen (the tracker starts at 0 / 1)
+        t = np.float32(np.arctan2(np.float64(d_neg), -np.float64(s_neg)))
+        if t > _F32_HALF_PI:
+            t = np.float32(t - _F32_PI)
+        best = max(best, np.float32(abs(t)))
+    return np.float32(best)
+
+
+def _vn_score(p: np.ndarray, angle_limit, lambda_mean, lambda_skew, lambda_correlation, lambda_penalty) -> np.float32:
+    denom = np.float32(np.float32(p[0]) + np.float32(EPSILON))  # radii.sum() + EPSILON, float32 (utils/dsp.py:418)
+    spread = float(np.float32(p[2] / np.float64(denom)))  # optimization.py:19-21
+    cen = float(np.float32(p[1] / np.float64(denom)))  # :24-26
+    m3 = float(np.float32(p[3] / np.float64(denom)))
+    skew = m3 / (max(spread, EPSILON) ** 1.5)  # :29-38
+    nl = np.float32(np.float32(np.sqrt(p[5])) + np.float32(EPSILON))  # :11-16, both channels over ||L||
+    corr = np.float32(p[4] / (np.float64(nl) * np.float64(nl)))
+    exceed = max(0.0, float(np.float32(_max_abs_theta_f32(p) - np.float32(angle_limit))))  # :41-43
+    mean_theta_penalty = lambda_mean * cen**2
+    skewness_penalty = lambda_skew * skew**2
+    lr_correlation_penalty = lambda_correlation * corr**2  # np.float32
+    constraint_penalty = lambda_penalty * exceed**2
+    objective = spread - mean_theta_penalty - skewness_penalty - lr_correlation_penalty - constraint_penalty
+    return -objective  # np.float32, like the reference for float32 decorrelator output
+
+
+def _haas_score(p: np.ndarray, angle_limit, lambda_mean, lambda_skew, lambda_correlation, lambda_penalty) -> np.float64:
+    denom = p[0] + EPSILON
+    spread = float(p[2] / denom)
+    cen = float(p[1] / denom)
+    skew = float(p[3] / denom) / (max(spread, EPSILON) ** 1.5)
+    nl = np.sqrt(p[6]) + EPSILON
+    corr = np.float64(p[5] / (nl * nl))
+    exceed = max(0.0, float(p[4] - angle_limit))
+    objective = spread - lambda_mean * cen**2 - lambda_skew * skew**2 - lambda_correlation * corr**2 - lambda_penalty * exceed**2
+    return np.float64(-objective)
+
+
+def vn_scores_from_partials(partials, **kw) -> np.ndarray:
+    p = partials.cpu().numpy() if R.is_torch_tensor(partials) else np.asarray(partials)
+    flat = p.reshape(-1, N.OBJ_SLOTS)
+    return np.array([_vn_score(row, **kw) for row in flat], dtype=np.float32).reshape(p.shape[:-1])
+
+
+def haas_scores_from_partials(partials, **kw) -> np.ndarray:
+    p = partials.cpu().numpy() if R.is_torch_tensor(partials) else np.asarray(partials)
+    flat = p.reshape(-1, N.HAAS_SLOTS)
+    return np.array([_haas_score(row, **kw) for row in flat], dtype=np.float64).reshape(p.shape[:-1])
+
+
+# ------------------------------------------------------------------------------------------------
+# candidate recognition
+# ------------------------------------------------------------------------------------------------
+
+
+def _is_vn_candidate(d) -> bool:
+    return (
+        isinstance(d, VelvetNoise) and d.num_outs == 2 and d.width is None and d.normalizer is None
+        and tuple(d.filtered_channels) == (0,) and _is_mode(d.mode, LayoutMode.LR)
+    )
+
+
+def _is_haas_candidate(d) -> bool:
+    return isinstance(d, HaasEffect) and d.width is None and _is_mode(d.mode, LayoutMode.LR) and d.delayed_channel == 0
+
+
+def _as_stereo_f32(input_signal):
+    x = np.asarray(input_signal).astype(np.float32, copy=False)
+    if x.ndim == 1:
+        x = np.column_stack((x, x))
+    if x.ndim != 2 or x.shape[1] < 2:
+        raise ValueError(f"Input shape invalid: Expected shape (num samples, 2), but got shape {x.shape}.")
+    return x[:, :2]
+
+
+def _vn_family_program(decorrelators: Sequence[VelvetNoise], frames: int) -> TapProgram | None:
+    env = decorrelators[0].segment_envelope
+    if any(d.segment_envelope != env for d in decorrelators):
+        return None
+    return candidate_program([d.velvet_noise for d in decorrelators], env, frames)
+
+
+_IDENTITY_PROGRAM_WORDS = np.array([1, 0, 1, np.float32(1.0).view(np.int32), 0], dtype=np.int32)  # one +1 tap at index 0
+
+
+def _score_signal(y, kw) -> Any:
+    """Objective of an already decorrelated stereo signal (generic decorrelators)."""
+    y = y.detach().cpu().numpy() if R.is_torch_tensor(y) else np.asarray(y)
+    if y.dtype == np.float32:
+        prog = TapProgram(_IDENTITY_PROGRAM_WORDS, np.array([0, 5], dtype=np.int32), 1, N.ORDER_SEGMENTED, 0, 1, 5)
+        return vn_scores_from_partials(vn_objective_partials(y[:, :2], prog), **kw)[0, 0]
+    return haas_scores_from_partials(haas_objective_partials(y[:, :2].astype(np.float64, copy=False), [0]), **kw)[0, 0]
+
+
+# ------------------------------------------------------------------------------------------------
+# public API (optimization.py:46-310)
+# ------------------------------------------------------------------------------------------------
+
+
+def symmetry_aware_objective(input_signal, decorrelator: Decorrelator, *, angle_limit: float, lambda_mean: float, lambda_skew: float,
+                             lambda_correlation: float, lambda_penalty: float):
+    """Value to minimise: ``-(E_w[th^2] - l1*E_w[th]^2 - l2*skew^2 - l3*r^2 - lp*exceed^2)``
+    for ``decorrelator`` applied to ``input_signal`` (optimization.py:46-105)."""
+    kw = dict(angle_limit=angle_limit, lambda_mean=lambda_mean, lambda_skew=lambda_skew, lambda_correlation=lambda_correlation,
+              lambda_penalty=lambda_penalty)
+    return _scan(input_signal, [decorrelator], kw)[0]
+
+
+def _scan(input_signal, decorrelators, kw) -> np.ndarray:
+    if len(decorrelators) == 0:
+        return np.array([])
+    if all(_is_vn_candidate(d) for d in decorrelators):
+        x = _as_stereo_f32(input_signal)
+        prog = _vn_family_program(decorrelators, x.shape[0])
+        if prog is not None:
+            return vn_scores_from_partials(vn_objective_partials(x, prog), **kw)[0]
+    if all(_is_haas_candidate(d) for d in decorrelators):
+        x = _as_stereo_f32(input_signal)
+        delays = [d.delay_len_samples for d in decorrelators]
+        return haas_scores_from_partials(haas_objective_partials(x, delays), **kw)[0]
+    return np.array([_score_signal(d.decorrelate(input_signal), kw) for d in decorrelators])
+
+
+def grid_scan(input_signal, decorrelators: list[Decorrelator], **kwargs) -> np.ndarray:
+    """Scores of all ``decorrelators`` on ``input_signal`` (optimization.py:108-117), one launch per
+    candidate family."""
+    print("Starting Grid Scan")
+    return _scan(input_signal, list(decorrelators), kwargs)
+
+
+def get_local_minima(scores, grid_size: int) -> list[int]:
+    """Strict interior local minima, or ``[argmin]`` if there are none (optimization.py:120-128)."""
+    local_minima = [i for i in range(1, grid_size - 1) if scores[i] < scores[i - 1] and scores[i] < scores[i + 1]]
+    if not local_minima:
+        return [int(np.argmin(scores))]
+    return local_minima
+
+
+def optimize_local_minima(local_minima: list[int], scalars, grid_size: int, scalar_objective: Callable[[float], float]):
+    """Bounded Brent (``xatol=1e-4``) between the grid neighbours of each local minimum; the first
+    strictly best result wins (optimization.py:131-155)."""
+    from scipy.optimize import minimize_scalar
+
+    best_scalar, best_score = 0.0, np.inf
+    print("Starting Local Minima optimization")
+    for i in local_minima:
+        low = scalars[max(0, i - 1)]
+        high = scalars[min(grid_size - 1, i + 1)]
+        result = minimize_scalar(fun=scalar_objective, bounds=(low, high), method="bounded", options={"xatol": 1e-4})
+        if result.fun < best_score:
+            best_score = result.fun
+            best_scalar = result.x
+    return best_scalar
+
+
+def optimize_haas_delay(*, input_signal, sample_rate_hz: int, max_delay_seconds: int, grid_size: int = 400, angle_limit: float = np.pi / 4,
+                        lambda_mean: float = 5.0, lambda_skew: float = 2.0, lambda_correlation: float = 15.0, lambda_penalty: float = 1e3) -> float:
+    """Optimised ``delay_time_seconds`` in ``[0, max_delay_seconds]`` (optimization.py:158-227)."""
+    kw = dict(angle_limit=angle_limit, lambda_mean=lambda_mean, lambda_skew=lambda_skew, lambda_correlation=lambda_correlation,
+              lambda_penalty=lambda_penalty)
+    taus = np.linspace(0.0, max_delay_seconds, grid_size)
+    candidates = [HaasEffect(sample_rate_hz=sample_rate_hz, delay_time_seconds=tau, mode="LR") for tau in taus]
+    scores = grid_scan(input_signal, candidates, **kw)
+    local_minima = get_local_minima(scores, grid_size)
+    return optimize_local_minima(
+        local_minima, taus, grid_size,
+        lambda tau: symmetry_aware_objective(input_signal, HaasEffect(sample_rate_hz=sample_rate_hz, delay_time_seconds=tau, mode="LR"), **kw),
+    )
+
+
+def optimize_velvet_noise(*, input_signal, sample_rate_hz: int, duration_seconds: float, num_impulses: int, seed: int = 1, grid_size: int = 400,
+                          angle_limit: float = np.pi / 4, lambda_mean: float = 5.0, lambda_skew: float = 2.0, lambda_correlation: float = 15.0,
+                          lambda_penalty: float = 1e3) -> float:
+    """Optimised ``log_distribution_strength`` in ``[0, 1]`` (optimization.py:230-310)."""
+    kw = dict(angle_limit=angle_limit, lambda_mean=lambda_mean, lambda_skew=lambda_skew, lambda_correlation=lambda_correlation,
+              lambda_penalty=lambda_penalty)
+
+    def candidate(kappa):
+        return VelvetNoise(sample_rate_hz=sample_rate_hz, duration_seconds=duration_seconds, num_impulses=num_impulses,
+                           log_distribution_strength=kappa, normalizer=None, filtered_channels=(0,), mode="LR", seed=seed)
+
+    kappas = np.linspace(0.0, 1.0, grid_size)
+    scores = grid_scan(input_signal, [candidate(k) for k in kappas], **kw)
+    local_minima = get_local_minima(scores, grid_size)
+    return optimize_local_minima(local_minima, kappas, grid_size, lambda kappa: symmetry_aware_objective(input_signal, candidate(kappa), **kw))
