@@ -211,7 +211,7 @@ def test_torch_tensors_match_numpy_path(api):
     assert G.same_bits(vn.decorrelate(mono).cpu().numpy(), vn.decorrelate(x[:, 0].copy()))
 
 
-@pytest.mark.parametrize("frames", [1, 255, 8191, 8192, 8193, 3 * 8192 + 5])
+@pytest.mark.parametrize("frames", [1, 255, 8191, 8192, 8193, 8447, 8448, 8449, 2 * 8448 - 1, 2 * 8448 + 1057, 3 * 8192 + 5, 5 * 8448])
 def test_planar_slab_tile_edges(api, frames):
     """cfg3-style planar slab (time contiguous per channel, the TMA bulk-copy path) around the
     tile boundaries of the kernel, against the oracle."""
@@ -227,6 +227,31 @@ def test_planar_slab_tile_edges(api, frames):
     taps = O.class_taps(sample_rate_hz=48000, num_outs=C, filtered_channels=tuple(range(C)), seed=1)
     want = O.fir_class_order(np.ascontiguousarray(slab.cpu().numpy().T), taps, O.DEFAULT_ENVELOPE, C)
     assert G.same_bits(np.ascontiguousarray(y.cpu().numpy()), want)
+
+
+@pytest.mark.parametrize("kappa,envelope", [(0.0, (0.85, 0.55, 0.35, 0.2)), (0.4, (1.0,)), (1.0, (0.9, -0.5)), (1.0, (0.85, 0.55, 0.35, 0.2))])
+def test_planar_slab_filter_shapes(api, kappa, envelope):
+    """Uniform and log-distributed impulses, identity / negative / default envelopes, and an output
+    slab whose base is not 16-byte aligned (no bulk store) on the register-window kernel."""
+    import torch
+
+    C, frames = 5, 40000
+    vn = api.VelvetNoise(sample_rate_hz=48000, num_outs=C, filtered_channels=(0, 1, 2, 3), mode="LR", normalizer=None,
+                         log_distribution_strength=kappa, segment_envelope=envelope, seed=3)
+    slab = torch.randn((C, frames), device="cuda") * 0.1
+    slab[2, 100:5000] = 0.0  # runs of exact zeros (signed-zero handling of the negated accumulation)
+    slab[2, 5000:5100] = -0.0
+    y = vn.convolve(slab.t())
+    taps = O.class_taps(sample_rate_hz=48000, num_outs=C, filtered_channels=(0, 1, 2, 3), num_segments=len(envelope),
+                        log_distribution_strength=kappa, seed=3)
+    want = O.fir_class_order(np.ascontiguousarray(slab.cpu().numpy().T), taps, envelope, C)
+    assert G.same_bits(np.ascontiguousarray(y.cpu().numpy()), want)
+    # same slab through a view that starts 4 bytes into a buffer: TMA-ineligible input and output
+    buf = torch.empty(C * frames + 1, device="cuda")
+    view = buf[1:].view(C, frames)
+    view.copy_(slab)
+    y2 = vn.convolve(view.t())
+    assert torch.equal(y2, y)
 
 
 def test_planar_slab_unaligned_falls_back(api):

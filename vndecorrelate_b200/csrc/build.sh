@@ -11,5 +11,6 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
   -Xcompiler -fPIC,-O2 -shared \
   ${VND_PTXAS_V:+-Xptxas -v} \
   -o "$out/libvnd_b200.so" \
-  "$here/vnd_abi.cu" "$here/vnd_fir.cu" "$here/vnd_post.cu" "$here/vnd_objective.cu"
+  ${VND_EXTRA_DEFS:-} \
+  "$here/vnd_abi.cu" "$here/vnd_fir.cu" "$here/vnd_fir_window.cu" "$here/vnd_post.cu" "$here/vnd_objective.cu"
 echo "built $out/libvnd_b200.so"

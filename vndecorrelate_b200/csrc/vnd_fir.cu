@@ -15,27 +15,12 @@
 // words (conflict-free LDS), and each of the R stores is one full 128-byte line.  Samples past the
 // end of the signal are staged as +0: adding +0 is bit-identical to the reference dropping the tap.
 
+#include <stdlib.h>
+
 #include "vnd_common.cuh"
+#include "vnd_fir.cuh"
 
 namespace vnd {
-
-enum { MODE_SEG = 0, MODE_ASC32 = 1, MODE_ASC64 = 2 };
-
-struct FirParams {
-  const void* x;
-  long long x_st, x_sc;
-  float* y;
-  long long y_st, y_sc;
-  long long frames;
-  int channels;
-  const int* words;
-  const int* offsets;
-  int tile;
-  int halo;
-  int tiles_per_channel;
-  int apply_gain;
-  int bulk_ok;
-};
 
 template <typename T>
 struct is_f64 { static constexpr bool value = false; };
@@ -345,6 +330,11 @@ __global__ void __launch_bounds__(256) vn_stereo_kernel(const StereoParams p) {
 // launchers
 // ------------------------------------------------------------------------------------------------
 constexpr int kR = 8;
+// VND_DISABLE_WINDOW=1 in the environment forces the general tile kernel (A/B runs and tests).
+static const bool g_disable_window = [] {
+  const char* e = getenv("VND_DISABLE_WINDOW");
+  return e && e[0] == '1';
+}();
 
 template <typename TIn, int MODE, int NT>
 static int launch_tile(const FirParams& p, size_t smem, cudaStream_t st) {
@@ -424,8 +414,13 @@ int sparse_fir_launch(const vnd_signal* x, const vnd_signal* y, const vnd_tap_pr
   // the halo never needs to reach past the end of the signal
   if (p.halo > p.frames) p.halo = (int)p.frames;
   p.halo = (p.halo + 3) & ~3;
-  p.tile = plan_tile(p.halo, elem, max_prog_words, p.frames, &nt, &smem);
   const int mode = taps->order == VND_ORDER_SEGMENTED ? MODE_SEG : (taps->order == VND_ORDER_ASCENDING ? MODE_ASC32 : MODE_ASC64);
+  p.bulk_ok = (!f64 && x->stride_t == 1 && (x->stride_c % 4) == 0 && (reinterpret_cast<uintptr_t>(x->data) % 16) == 0) ? 1 : 0;
+  if (!f64 && mode == MODE_SEG && !g_disable_window) {  // throughput path for planar float32 slabs
+    const int rc = fir_window_launch(p, max_prog_words, st);
+    if (rc != VND_EUNSUPPORTED) return rc;
+  }
+  p.tile = plan_tile(p.halo, elem, max_prog_words, p.frames, &nt, &smem);
   if (p.tile == 0) {
     if (f64) {
       if (mode == MODE_SEG) return launch_direct<double, MODE_SEG>(p, st);
@@ -436,7 +431,6 @@ int sparse_fir_launch(const vnd_signal* x, const vnd_signal* y, const vnd_tap_pr
     return launch_direct<float, MODE_ASC64>(p, st);
   }
   p.tiles_per_channel = (int)ceil_div<long long>(p.frames, p.tile);
-  p.bulk_ok = (!f64 && x->stride_t == 1 && (x->stride_c % 4) == 0 && (reinterpret_cast<uintptr_t>(x->data) % 16) == 0) ? 1 : 0;
   if (f64) {
     if (mode == MODE_SEG) return launch_tile_nt<double, MODE_SEG>(p, smem, nt, st);
     return launch_tile_nt<double, MODE_ASC64>(p, smem, nt, st);

@@ -1,0 +1,31 @@
+// Parameter block shared by the sparse-FIR kernels.
+#pragma once
+
+#include "vnd_common.cuh"
+
+namespace vnd {
+
+enum { MODE_SEG = 0, MODE_ASC32 = 1, MODE_ASC64 = 2 };
+
+struct FirParams {
+  const void* x;
+  long long x_st, x_sc;
+  float* y;
+  long long y_st, y_sc;
+  long long frames;
+  int channels;
+  const int* words;
+  const int* offsets;
+  int tile;
+  int halo;
+  int tiles_per_channel;
+  int apply_gain;
+  int bulk_ok;
+};
+
+
+// vnd_fir_window.cu: the register-window variant for planar float32 SEGMENTED programs.  Returns
+// VND_EUNSUPPORTED (no error text) when the request does not qualify.
+int fir_window_launch(const FirParams& p, int max_prog_words, cudaStream_t st);
+
+}  // namespace vnd
