@@ -297,9 +297,10 @@ def run_b200(args) -> None:
             traffic = tr["dram_bytes_per_sample"] * Cg * L
         except Exception:
             traffic = None
+    kernel_name = "fir_tile_kernel<float,SEGMENTED>" if os.environ.get("VND_DISABLE_WINDOW") == "1" else "fir_window_kernel<R=29,W=32> (register-window, persistent, TMA double-buffered)"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "fir_tile_kernel<float, SEGMENTED>", "kernel_ms": kernel_ms, "peak_source": peak_src,
-                "note": "binding resource is the shared-memory (LSU) pipe: 30 x 4 B per output sample at 128 B/clk/SM; see DESIGN.md"}
+                "kernel": kernel_name, "kernel_ms": kernel_ms, "peak_source": peak_src,
+                "lsu_pipe_frac": None, "note": "HBM is not the binding resource: every (output, tap) pair moves 4 B from shared memory (128 B/clk/SM); ncu shows that pipe 75-88 % busy with DRAM at 22-25 %. See DESIGN.md section 4 and profiles/r01_summary.md"}
 
     # end to end through the C ABI with HOST buffers (copies inside the timed region)
     e2e = None
