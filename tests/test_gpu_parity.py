@@ -254,6 +254,41 @@ def test_planar_slab_filter_shapes(api, kappa, envelope):
     assert torch.equal(y2, y)
 
 
+@pytest.mark.parametrize(
+    "frames,kappa,envelope,duration",
+    [
+        (140 * 128 + 3 * 16384, 1.0, (0.85, 0.55, 0.35, 0.2), 0.03),  # the shortest slab the kernel takes: 4 interior tiles
+        (140 * 128 + 3 * 16384 + 1, 1.0, (0.85, 0.55, 0.35, 0.2), 0.03),
+        (200003, 0.0, (0.85, 0.55, 0.35, 0.2), 0.03),  # uniform impulses: most taps beyond the TMEM window
+        (150000, 0.4, (1.0,), 0.03),  # identity envelope (no gain multiply), one segment
+        (131072 + 9000, 1.0, (0.9, -0.5), 0.03),
+        (300001, 1.0, (0.85, 0.55, 0.35, 0.2), 0.06),  # 2 880-sample halo: more staged blocks per tile
+        (180000, 1.0, (0.85, 0.55, 0.35, 0.2), 0.004),  # every tap inside the TMEM window
+    ],
+)
+def test_planar_slab_tmem_kernel(api, frames, kappa, envelope, duration):
+    """Long planar slabs take the tensor-memory kernel for the interior tiles and the tile kernel
+    for the tail of each channel; the whole output must equal the oracle bit for bit."""
+    import torch
+
+    C = 5
+    filtered = (0, 1, 2, 3)  # channel 4 is copied through
+    vn = api.VelvetNoise(sample_rate_hz=48000, duration_seconds=duration, num_impulses=30, num_outs=C, filtered_channels=filtered,
+                         mode="LR", normalizer=None, log_distribution_strength=kappa, segment_envelope=envelope, seed=5)
+    g = torch.Generator(device="cuda").manual_seed(99)
+    slab = torch.randn((C, frames), generator=g, device="cuda") * 0.1
+    slab[1, 20000:26000] = 0.0
+    slab[1, 26000:26100] = -0.0
+    y = vn.convolve(slab.t())
+    taps = O.class_taps(sample_rate_hz=48000, duration_seconds=duration, num_impulses=30, num_outs=C, filtered_channels=filtered,
+                        num_segments=len(envelope), log_distribution_strength=kappa, seed=5)
+    want = O.fir_class_order(np.ascontiguousarray(slab.cpu().numpy().T), taps, envelope, C)
+    got = np.ascontiguousarray(y.cpu().numpy())
+    if not G.same_bits(got, want):
+        bad = np.argwhere(got.view(np.uint32) != want.view(np.uint32))
+        raise AssertionError(f"{len(bad)} samples differ; first at (frame, channel) {bad[0]}, last {bad[-1]}")
+
+
 def test_planar_slab_unaligned_falls_back(api):
     """A channel stride that is not a multiple of 4 samples cannot use the bulk copy."""
     import torch

@@ -336,6 +336,12 @@ static const bool g_disable_window = [] {
   return e && e[0] == '1';
 }();
 
+// VND_DISABLE_TMEM=1 skips the tensor-memory kernel (A/B runs and tests).
+static const bool g_disable_tmem = [] {
+  const char* e = getenv("VND_DISABLE_TMEM");
+  return e && e[0] == '1';
+}();
+
 template <typename TIn, int MODE, int NT>
 static int launch_tile(const FirParams& p, size_t smem, cudaStream_t st) {
   auto k = fir_tile_kernel<TIn, MODE, NT, kR>;
@@ -416,7 +422,20 @@ int sparse_fir_launch(const vnd_signal* x, const vnd_signal* y, const vnd_tap_pr
   p.halo = (p.halo + 3) & ~3;
   const int mode = taps->order == VND_ORDER_SEGMENTED ? MODE_SEG : (taps->order == VND_ORDER_ASCENDING ? MODE_ASC32 : MODE_ASC64);
   p.bulk_ok = (!f64 && x->stride_t == 1 && (x->stride_c % 4) == 0 && (reinterpret_cast<uintptr_t>(x->data) % 16) == 0) ? 1 : 0;
-  if (!f64 && mode == MODE_SEG && !g_disable_window) {  // throughput path for planar float32 slabs
+  if (!f64 && mode == MODE_SEG && !g_disable_tmem) {  // throughput path for long planar float32 slabs
+    long long done = 0;
+    const int rc = fir_tmem_launch(p, max_prog_words, st, &done);
+    if (rc != VND_OK && rc != VND_EUNSUPPORTED) return rc;
+    if (rc == VND_OK && done > 0) {  // the tail of every channel goes through the kernels below
+      p.x = reinterpret_cast<const float*>(p.x) + done;
+      p.y += done;
+      p.frames -= done;
+      if (p.frames == 0) return VND_OK;
+      if (p.halo > p.frames) p.halo = (int)((p.frames + 3) & ~3LL);
+      p.bulk_ok = (p.bulk_ok && (reinterpret_cast<uintptr_t>(p.x) % 16) == 0) ? 1 : 0;
+    }
+  }
+  if (!f64 && mode == MODE_SEG && !g_disable_window) {  // planar float32 slabs too short for the above
     const int rc = fir_window_launch(p, max_prog_words, st);
     if (rc != VND_EUNSUPPORTED) return rc;
   }

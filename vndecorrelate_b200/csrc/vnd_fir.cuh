@@ -28,4 +28,9 @@ struct FirParams {
 // VND_EUNSUPPORTED (no error text) when the request does not qualify.
 int fir_window_launch(const FirParams& p, int max_prog_words, cudaStream_t st);
 
+// vnd_fir_tmem.cu: the tensor-memory variant for planar float32 SEGMENTED programs.  Covers the
+// interior tiles of every channel and reports the frames done per channel; the caller finishes the
+// tail.  Returns VND_EUNSUPPORTED (no error text) when the request does not qualify.
+int fir_tmem_launch(const FirParams& p, int max_prog_words, cudaStream_t st, long long* frames_done);
+
 }  // namespace vnd
