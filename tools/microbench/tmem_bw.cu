@@ -78,7 +78,23 @@ __device__ __forceinline__ void ldtm(uint32_t (&v)[N], uint32_t taddr) {
   else ldtm64(v, taddr);
 }
 
-enum Mode { LDTM = 0, LDS = 1, MIXED = 2, STTM = 3, LDTM_NOWAIT2 = 4 };
+enum Mode { LDTM = 0, LDS = 1, MIXED = 2, STTM = 3, LDTM_NOWAIT2 = 4, FADD1 = 5, FADD2 = 6, LDTM_FADD2 = 7 };
+
+// packed fp32 add/sub (sm_100+): two IEEE round-to-nearest adds per instruction (FADD2 in SASS)
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+  unsigned long long ra, rb;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(ra) : "l"(rb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(ra));
+}
+__device__ __forceinline__ void sub2(float& a0, float& a1, float b0, float b1) {
+  unsigned long long ra, rb;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));
+  asm("sub.rn.f32x2 %0, %0, %1;" : "+l"(ra) : "l"(rb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(ra));
+}
 
 struct Result {
   unsigned long long cycles;
@@ -175,6 +191,35 @@ __global__ void __launch_bounds__(NW * 32, 1) bench_kernel(int iters, Result* ou
 #pragma unroll
       for (int j = 0; j < N; ++j) acc[j] = __fadd_rn(acc[j], __uint_as_float(v[j]));
     }
+  } else if constexpr (MODE == FADD1) {  // pure FADD issue rate: N independent chains
+    float b = (float)lane;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) acc[j] = __fadd_rn(acc[j], b);
+      b = b + 1.0f;
+    }
+  } else if constexpr (MODE == FADD2) {  // the same adds as N/2 packed instructions
+    float b = (float)lane;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int j = 0; j < N; j += 2) {
+        if (it & 1) sub2(acc[j], acc[j + 1], b, b);
+        else add2(acc[j], acc[j + 1], b, b);
+      }
+      b = b + 1.0f;
+    }
+  } else if constexpr (MODE == LDTM_FADD2) {
+    for (int it = 0; it < iters; it += 2) {
+      const int off = offs[it & 63], off2 = offs[(it + 1) & 63];
+      uint32_t v[N], u[N];
+      ldtm<N>(v, tbase + off);
+      ldtm<N>(u, tbase + off2);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < N; j += 2) add2(acc[j], acc[j + 1], __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+#pragma unroll
+      for (int j = 0; j < N; j += 2) sub2(acc[j], acc[j + 1], __uint_as_float(u[j]), __uint_as_float(u[j + 1]));
+    }
   } else if constexpr (MODE == STTM) {
     if constexpr (N == 32) {
       uint32_t v[32];
@@ -247,6 +292,12 @@ void all(int iters, Result* d_out, int sms) {
   if constexpr (NW <= 16) run<32, MIXED, NW>("mixed", iters, d_out, sms);
   else run<16, MIXED, NW>("mixed", iters, d_out, sms);
   run<32, STTM, NW>("sttm", iters, d_out, sms);
+  if constexpr (NW <= 16) {
+    run<32, FADD1, NW>("fadd", iters, d_out, sms);
+    run<32, FADD2, NW>("fadd2", iters, d_out, sms);
+    run<16, LDTM_FADD2, NW>("ldtm+f2", iters, d_out, sms);
+    run<32, LDTM_FADD2, NW>("ldtm+f2", iters, d_out, sms);
+  }
 }
 
 int main() {

@@ -1,0 +1,7 @@
+#!/usr/bin/env bash
+# Parity of the tensor-memory kernel + a short cfg3 bench (run on the GPU box).
+cd "$(dirname "$0")/.."
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "tmem or size_independent" 2>&1 | tail -4
+timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --channels-per-gpu ${CH:-64} --e2e-channels 2 2>&1 | tail -1 | python -c "
+import sys, json
+d = json.loads(sys.stdin.read()); print('%.1f Gs/s  frac %.3f  clk %s  parity %s' % (d['value'], d['roofline']['frac'], d['clocks']['sm_mhz'], d['config']['parity_spot_check'][:9]))"

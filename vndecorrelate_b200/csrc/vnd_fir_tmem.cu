@@ -102,55 +102,116 @@ struct TmParams {
   long long tiles_per_channel;  // interior tiles
 };
 
-// A tap served from tensor memory: acc (-|+)= x[n + i] for the thread's 32 outputs.
-template <bool SUB>
-__device__ __forceinline__ void near_tap(uint32_t tcol, float (&acc)[kRG]) {
+// ---- packed fp32 arithmetic (sm_100+): FADD2 / FMUL2 do two IEEE round-to-nearest operations per
+// instruction on an aligned register pair.  Same bits as two scalar operations, half the issue
+// slots — and issue slots, not the FP32 pipe, are what this kernel runs out of.
+typedef unsigned long long pair_t;
+__device__ __forceinline__ pair_t pk(float a, float b) {
+  pair_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk(pair_t r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+// In-place forms ("+l"): with a separate destination ptxas writes the result over the loaded operand
+// and copies it back into the accumulator pair (32 extra moves per tap).
+__device__ __forceinline__ pair_t add2(pair_t a, pair_t b) {
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+  return a;
+}
+__device__ __forceinline__ pair_t sub2(pair_t a, pair_t b) {
+  asm("sub.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+  return a;
+}
+__device__ __forceinline__ pair_t mul2(pair_t a, pair_t b) {
+  asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+  return a;
+}
+constexpr int kNP = kRG / 2;  // register pairs per thread
+
+__device__ __forceinline__ void bar_quarter(int q) { asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory"); }
+
+// The negative list is accumulated with adds and negated once at the end of the list:
+// fl(-a - b) == -fl(a + b) in round-to-nearest, and a zero of the other sign cannot survive into the
+// output (the running output is never -0).  One add body per datapath.
+
+// A tap served from tensor memory: acc += x[n + i] for the thread's 32 outputs.
+__device__ __forceinline__ void near_tap(uint32_t tcol, pair_t (&acc)[kNP]) {
   float t[kRG];
   tmem_ld16<0>(t, tcol);
   tmem_ld16<16>(t, tcol + 16);
   tmem_wait_ld(t);
 #pragma unroll
-  for (int r = 0; r < kRG; ++r) acc[r] = SUB ? fsub(acc[r], t[r]) : fadd(acc[r], t[r]);
+  for (int j = 0; j < kNP; ++j) acc[j] = add2(acc[j], pk(t[2 * j], t[2 * j + 1]));
 }
 
 // A tap served from shared memory.  `row` points at the staged block of this thread's row; `o` is
 // the offset of the thread's first operand relative to it (32 g + i); A = o & 3 is warp-uniform.
 // The 32 operands lie in 8 (A == 0) or 9 aligned 16-byte chunks; the run crosses at most one block
-// boundary, where the pitch inserts a 4-word gap.
-template <int A, bool SUB>
-__device__ __forceinline__ void far_tap_a(const float* __restrict__ row, int o, float (&acc)[kRG]) {
+// boundary, where the pitch inserts a 4-word gap: KX = chunks before the gap.
+template <int NC, int KX>
+__device__ __forceinline__ void far_load(const float4* __restrict__ p, float4 (&c)[NC]) {
+#pragma unroll
+  for (int k = 0; k < NC; ++k) c[k] = p[k + (k >= KX ? 1 : 0)];
+}
+
+template <int A>
+__device__ __forceinline__ void far_tap_a(const float* __restrict__ row, int o, pair_t (&acc)[kNP]) {
   constexpr int NC = (A == 0) ? 8 : 9;
   const int oal = o - A;
   const int w = oal & (kR - 1);
   const float4* p = reinterpret_cast<const float4*>(row + (oal >> 7) * kPitch + w);
-  const int kx = (kR - w) >> 2;  // chunks before the gap
+  const int kx = (kR - w) >> 2;  // >= 1
+  float4 c[NC];
+  if (kx >= NC) {
+    far_load<NC, NC>(p, c);
+  } else {  // static addressing per crossing position
+    switch (kx) {
+      case 1: far_load<NC, 1>(p, c); break;
+      case 2: far_load<NC, 2>(p, c); break;
+      case 3: far_load<NC, 3>(p, c); break;
+      case 4: far_load<NC, 4>(p, c); break;
+      case 5: far_load<NC, 5>(p, c); break;
+      case 6: far_load<NC, 6>(p, c); break;
+      case 7: far_load<NC, 7>(p, c); break;
+      default: far_load<NC, 8>(p, c); break;
+    }
+  }
   float t[NC * 4];
 #pragma unroll
   for (int k = 0; k < NC; ++k) {
-    const float4 v = (k < kx ? p : p + 1)[k];
-    t[4 * k] = v.x;
-    t[4 * k + 1] = v.y;
-    t[4 * k + 2] = v.z;
-    t[4 * k + 3] = v.w;
+    t[4 * k] = c[k].x;
+    t[4 * k + 1] = c[k].y;
+    t[4 * k + 2] = c[k].z;
+    t[4 * k + 3] = c[k].w;
   }
+  if constexpr (A % 2 == 0) {  // operands arrive as aligned register pairs
 #pragma unroll
-  for (int r = 0; r < kRG; ++r) acc[r] = SUB ? fsub(acc[r], t[r + A]) : fadd(acc[r], t[r + A]);
-}
-
-template <bool SUB>
-__device__ __forceinline__ void far_tap(const float* __restrict__ row, int o, float (&acc)[kRG]) {
-  switch (o & 3) {
-    case 0: far_tap_a<0, SUB>(row, o, acc); break;
-    case 1: far_tap_a<1, SUB>(row, o, acc); break;
-    case 2: far_tap_a<2, SUB>(row, o, acc); break;
-    default: far_tap_a<3, SUB>(row, o, acc); break;
+    for (int j = 0; j < kNP; ++j)
+      acc[j] = add2(acc[j], pk(t[2 * j + A], t[2 * j + 1 + A]));
+  } else {  // odd shift: the pairs of the loaded data straddle the accumulator pairs -> scalar adds
+#pragma unroll
+    for (int j = 0; j < kNP; ++j) {
+      float a0, a1;
+      upk(acc[j], a0, a1);
+      a0 = fadd(a0, t[2 * j + A]);
+      a1 = fadd(a1, t[2 * j + 1 + A]);
+      acc[j] = pk(a0, a1);
+    }
   }
 }
 
-template <bool SUB>
-__device__ __forceinline__ void one_tap(int i, int g, uint32_t tbase, const float* __restrict__ row, float (&acc)[kRG]) {
-  if (i <= kNearMax) near_tap<SUB>(tbase + (uint32_t)(i + kRG * g), acc);
-  else far_tap<SUB>(row, i + kRG * g, acc);
+__device__ __forceinline__ void far_tap(const float* __restrict__ row, int o, pair_t (&acc)[kNP]) {
+  switch (o & 3) {
+    case 0: far_tap_a<0>(row, o, acc); break;
+    case 1: far_tap_a<1>(row, o, acc); break;
+    case 2: far_tap_a<2>(row, o, acc); break;
+    default: far_tap_a<3>(row, o, acc); break;
+  }
+}
+
+__device__ __forceinline__ void one_tap(int i, int og, uint32_t tcol0, const float* __restrict__ row, pair_t (&acc)[kNP]) {
+  if (i <= kNearMax) near_tap(tcol0 + (uint32_t)i, acc);
+  else far_tap(row, i + og, acc);
 }
 
 // Shared memory: [0,16) two mbarriers | [16,20) TMEM base | [64, ...) float in[2][nblk][132] |
@@ -180,21 +241,22 @@ __global__ void __launch_bounds__(kNT, 1) fir_tmem_kernel(const TmParams P) {
   __syncthreads();
   tmem_fence_after();
   const uint32_t tbase = *tm_slot + ((uint32_t)(32 * q) << 16);
-  unsigned use0 = 0, use1 = 0;  // fills of each tile buffer so far (mbarrier phase)
+  const uint32_t tcol0 = tbase + (uint32_t)(kRG * g);  // column of this thread's first output
+  unsigned phases = 0;  // bit b: parity of the next completion of tile buffer b
   bool pending_store = false;
 
-  for (long long run = blockIdx.x; run < P.n_runs; run += gridDim.x) {
-    const int c = (int)(run / P.runs_per_channel);
-    const long long first_tile = (run % P.runs_per_channel) * (long long)P.tiles_per_run;
-    long long n_tiles = P.tiles_per_channel - first_tile;
+  for (int run = blockIdx.x; run < (int)P.n_runs; run += gridDim.x) {
+    const int c = run / P.runs_per_channel;
+    const int first_tile = (run % P.runs_per_channel) * P.tiles_per_run;
+    int n_tiles = (int)P.tiles_per_channel - first_tile;
     if (n_tiles > P.tiles_per_run) n_tiles = P.tiles_per_run;
     const int w0 = p.offsets[c];
     const int nprog = p.offsets[c + 1] - w0;
-    const float* __restrict__ xc = reinterpret_cast<const float*>(p.x) + (long long)c * p.x_sc;
-    float* __restrict__ yc = p.y + (long long)c * p.y_sc;
 
     if (nprog == 0) {  // unfiltered channel: copy through (decorrelation.py:399-400)
-      const long long t_begin = first_tile * kTile, t_end = t_begin + n_tiles * kTile;
+      const float* xc = reinterpret_cast<const float*>(p.x) + (long long)c * p.x_sc;
+      float* yc = p.y + (long long)c * p.y_sc;
+      const long long t_begin = (long long)first_tile * kTile, t_end = t_begin + (long long)n_tiles * kTile;
       for (long long t = t_begin + 4 * tid; t < t_end; t += 4 * kNT)
         *reinterpret_cast<float4*>(yc + t) = *reinterpret_cast<const float4*>(xc + t);
       continue;
@@ -202,35 +264,29 @@ __global__ void __launch_bounds__(kNT, 1) fir_tmem_kernel(const TmParams P) {
 
     __syncthreads();  // everyone is done with the previous run's program
     for (int i = tid; i < nprog; i += kNT) sprog[i] = p.words[w0 + i];
+    if (tid == 0) sprog[nprog] = 0;  // slack word read by the tap prefetch
 
-    // one 512-byte bulk copy per 128-sample block, spread over the lanes of warp 0
-    auto issue = [&](long long ti, int buf) {
-      if (warp == 0) {
-        const float* src = xc + (first_tile + ti) * kTile;
-        float* dst = in_all + buf * bufw;
-        if (lane == 0) {
-          fence_proxy_async();
-          mbar_expect_tx(&bars[buf], (uint32_t)P.nblk * (kR * 4u));
-        }
-        __syncwarp();
-        for (int b = lane; b < P.nblk; b += 32) bulk_g2s(dst + b * kPitch, src + b * kR, kR * 4u, &bars[buf]);
+    // one 512-byte bulk copy per 128-sample block.  UBLKCP is issued lane by lane, so the blocks are
+    // dealt out to all warps (block b -> warp b % 16, lane b / 16): nine short issues per warp.
+    auto issue = [&](int ti, int buf) {
+      const float* src = reinterpret_cast<const float*>(p.x) + (long long)c * p.x_sc + (long long)(first_tile + ti) * kTile;
+      float* dst = in_all + buf * bufw;
+      if (tid == 0) mbar_expect_tx(&bars[buf], (uint32_t)P.nblk * (kR * 4u));
+      const int b = warp + kNW * lane;
+      if (b < P.nblk) {
+        fence_proxy_async();
+        bulk_g2s(dst + b * kPitch, src + b * kR, kR * 4u, &bars[buf]);
       }
     };
     issue(0, 0);
     __syncthreads();  // program visible
     const int S = sprog[0];
-    const int* seg = sprog + 1;
 
-    for (long long ti = 0; ti < n_tiles; ++ti) {
-      const int buf = (int)(ti & 1);
+    for (int ti = 0; ti < n_tiles; ++ti) {
+      const int buf = ti & 1;
       if (ti + 1 < n_tiles) issue(ti + 1, buf ^ 1);  // that buffer was released by the last barrier
-      if (buf == 0) {
-        mbar_wait(&bars[0], use0 & 1);
-        ++use0;
-      } else {
-        mbar_wait(&bars[1], use1 & 1);
-        ++use1;
-      }
+      mbar_wait(&bars[buf], (phases >> buf) & 1u);
+      phases ^= 1u << buf;
       const float* in = in_all + buf * bufw;
       const float* row = in + m * kPitch;
 
@@ -247,59 +303,80 @@ __global__ void __launch_bounds__(kNT, 1) fir_tmem_kernel(const TmParams P) {
         tmem_wait_st();
       }
       tmem_fence_before();
-      __syncthreads();
+      bar_quarter(q);  // TMEM lanes are private to a lane quarter: its four warps are the only users
       tmem_fence_after();
 
       // ---- taps, in the reference's order: per segment the negative list, then the positive ----
-      float yv[kRG];
-      const int* tp = sprog + 1 + 3 * S;
-      for (int s = 0; s < S; ++s) {
-        const int n_neg = seg[3 * s], n_pos = seg[3 * s + 1];
-        float acc[kRG];
+      pair_t yv[kNP];
+      {
+        const int* seg = sprog + 1;
+        const int* tp = sprog + 1 + 3 * S;
+        for (int s = 0; s < S; ++s) {
+          const int n_neg = seg[3 * s], n_pos = seg[3 * s + 1];
+          pair_t acc[kNP];
 #pragma unroll
-        for (int r = 0; r < kRG; ++r) acc[r] = 0.0f;
-        for (int k = 0; k < n_neg; ++k) one_tap<true>(tp[k], g, tbase, row, acc);
-        tp += n_neg;
-        for (int k = 0; k < n_pos; ++k) one_tap<false>(tp[k], g, tbase, row, acc);
-        tp += n_pos;
-        if (p.apply_gain) {
-          const float gain = __int_as_float(seg[3 * s + 2]);
+          for (int j = 0; j < kNP; ++j) acc[j] = 0ull;
+          int i_next = tp[0];  // one word of slack follows the program, so the prefetches stay in bounds
+          const int n_tot = n_neg + n_pos;
+          for (int k = 0; k < n_tot; ++k) {
+            const int i = i_next;
+            i_next = tp[k + 1];
+            one_tap(i, kRG * g, tcol0, row, acc);
+            if (k + 1 == n_neg) {  // end of the negative list: acc = -(sum of its taps)
+              const pair_t m1 = pk(-1.0f, -1.0f);
 #pragma unroll
-          for (int r = 0; r < kRG; ++r) acc[r] = fmul(acc[r], gain);
+              for (int j = 0; j < kNP; ++j) acc[j] = mul2(acc[j], m1);
+            }
+          }
+          tp += n_tot;
+          if (p.apply_gain) {
+            const float gain = __int_as_float(seg[3 * s + 2]);
+            const pair_t g2 = pk(gain, gain);
+#pragma unroll
+            for (int j = 0; j < kNP; ++j) acc[j] = mul2(acc[j], g2);
+          }
+          if (s == 0) {
+#pragma unroll
+            for (int j = 0; j < kNP; ++j) yv[j] = add2(acc[j], 0ull);  // the reference adds into zeros
+          } else {
+#pragma unroll
+            for (int j = 0; j < kNP; ++j) yv[j] = add2(yv[j], acc[j]);
+          }
         }
-        if (s == 0) {
+        if (S == 0) {
 #pragma unroll
-          for (int r = 0; r < kRG; ++r) yv[r] = fadd(0.0f, acc[r]);  // the reference adds into zeros
-        } else {
-#pragma unroll
-          for (int r = 0; r < kRG; ++r) yv[r] = fadd(yv[r], acc[r]);
+          for (int j = 0; j < kNP; ++j) yv[j] = 0ull;
         }
-      }
-      if (S == 0) {
-#pragma unroll
-        for (int r = 0; r < kRG; ++r) yv[r] = 0.0f;
       }
 
       // ---- output: staging rows at pitch 132, then one 512-byte bulk store per row ----
-      if (warp < 4 && pending_store) bulk_wait_read0();  // the staging buffer is free again
+      if (lane < 8 && pending_store) bulk_wait_read0();  // this warp's staging rows are free again
       tmem_fence_before();
-      __syncthreads();  // also: every tcgen05.ld of this tile is done before the next fill
+      bar_quarter(q);  // every tcgen05.ld of this quarter is done (next fill), its staging rows are free
       tmem_fence_after();
       {
         float4* dst = reinterpret_cast<float4*>(stage + m * kPitch + kRG * g);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_float4(yv[4 * j], yv[4 * j + 1], yv[4 * j + 2], yv[4 * j + 3]);
+        for (int j = 0; j < 8; ++j) {
+          float4 v;
+          upk(yv[2 * j], v.x, v.y);
+          upk(yv[2 * j + 1], v.z, v.w);
+          dst[j] = v;
+        }
       }
       fence_proxy_async();
-      __syncthreads();  // staging complete; all reads of this tile buffer are done
-      if (warp < 4) {
-        bulk_s2g(yc + (first_tile + ti) * kTile + (long long)m * kR, stage + m * kPitch, kR * 4u);
+      bar_quarter(q);  // staging rows of this quarter are complete
+      if (lane < 8) {  // row 32 q + 8 g + lane: eight 512-byte stores per warp
+        const int sr = 32 * q + 8 * g + lane;
+        float* yt = p.y + (long long)c * p.y_sc + (long long)(first_tile + ti) * kTile;
+        bulk_s2g(yt + sr * kR, stage + sr * kPitch, kR * 4u);
         bulk_commit();
         pending_store = true;
       }
+      __syncthreads();  // all reads of this tile buffer are done: it may be refilled
     }
   }
-  if (warp < 4 && pending_store) bulk_wait_read0();  // shared memory must outlive the bulk reads
+  if (lane < 8 && pending_store) bulk_wait_read0();  // shared memory must outlive the bulk reads
   tmem_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc_all(*tm_slot);
