@@ -10,21 +10,24 @@
 // into the register file: tcgen05.ld from tensor memory, measured at >= 390 B/clk/SM
 // (tools/microbench/tmem_bw.cu) and independent of the LSU pipe.  tcgen05.ld.32x32b hands lane l
 // of a warp N CONSECUTIVE columns of TMEM lane (row) l starting at a run-time column — exactly
-// "R consecutive samples starting at a tap offset" if row l holds the samples that follow the
+// "32 consecutive samples starting at a tap offset" if row l holds the samples that follow the
 // first output of lane l.
 //
-// Layout.  A tile is 128 rows x R = 128 outputs.  TMEM row m (512 columns x 4 B) holds
-// x[t0 + 128 m + c], c in [0, 512): a Hankel arrangement, each sample stored four times.  Thread
-// (row m, group g) owns outputs 128 m + 32 g + r, r < 32; a tap with offset i <= 384 is one
-// tcgen05.ld of 32 columns at column i + 32 g followed by 32 FADDs.  With log-distributed impulses
-// 22 of the 30 taps of BASELINE config 3 qualify.  The remaining (far) taps read the staged tile
-// from shared memory with 16-byte loads.
+// Layout.  A tile is 128 rows x R = 96 outputs.  TMEM row m (512 columns x 4 B) holds
+// x[t0 + 96 m + c], c in [0, 512): a Hankel arrangement.  Compute thread (row m, group g < 3)
+// owns outputs 96 m + 32 g + r, r < 32; a tap with offset i <= 416 is one 32-column tcgen05.ld at
+// column i + 32 g followed by 16 packed adds (FADD2).  With log-distributed impulses 22 of the 30
+// taps of BASELINE config 3 qualify.  The remaining (far) taps read the staged tile from shared
+// memory with 16-byte loads.  Shared memory holds the tile as 96-sample blocks at a pitch of 100
+// words, so that lanes (rows) hit distinct bank groups with LDS.128 / STS.128: one 384-byte TMA
+// bulk copy per block.
 //
-// Shared memory holds the tile as 128-sample blocks at a pitch of 132 words, so that lanes (rows
-// 128 samples apart) hit distinct bank groups with LDS.128 / STS.128: one 512-byte TMA bulk copy
-// per block.  Traffic on the LSU pipe per output: 4 words to fill TMEM (LDS.128 -> tcgen05.st),
-// ~1.1 words per far tap, 1 word of output staging (STS.128 -> TMA bulk store), against ~27 for
-// the register-window kernel.
+// Roles (one CTA of 16 warps per SM; warp w works on TMEM lane quarter w & 3, which is also its
+// scheduler).  Warps 0-11 compute (setmaxnreg 152).  Warps 12-15, one per quarter, are helpers
+// (setmaxnreg 56): they issue the bulk loads, fill TMEM for the next tile (LDS.128 ->
+// tcgen05.st) as soon as the quarter's compute warps are past their last TMEM tap — i.e. while
+// those warps run the trailing all-far segments and stage their outputs — and issue the bulk
+// stores.  Everything is handed over through mbarriers; there is no CTA-wide barrier inside a run.
 //
 // The kernel only runs interior tiles (tile + halo completely inside the signal); the launcher
 // reports how many frames it covered and the caller finishes the tail of every channel with the
@@ -33,8 +36,11 @@
 #include "vnd_common.cuh"
 #include "vnd_fir.cuh"
 
+#ifndef VND_TM_DOUBLE
+#define VND_TM_DOUBLE 0  // 1: tensor-memory loads issued one tap ahead into a second register buffer
+#endif
 #ifndef VND_TM_RUN
-#define VND_TM_RUN 32  // consecutive tiles of one channel per CTA run
+#define VND_TM_RUN 64  // consecutive tiles of one channel per CTA run
 #endif
 
 namespace vnd {
@@ -42,17 +48,24 @@ namespace vnd {
 namespace {
 
 constexpr int kRows = 128;             // TMEM lanes = rows of a tile
-constexpr int kR = 128;                // outputs per row
-constexpr int kG = 4;                  // thread groups per row
+constexpr int kR = 96;                 // outputs per row
+constexpr int kG = 3;                  // compute warps per lane quarter
 constexpr int kRG = kR / kG;           // outputs per thread
-constexpr int kNW = 4 * kG;            // warps per CTA (warp w: lane quarter w & 3, group w >> 2)
+constexpr int kNP = kRG / 2;           // register pairs per thread
+constexpr int kCW = 4 * kG;            // compute warps (warp w: lane quarter w & 3, group w >> 2)
+constexpr int kNW = kCW + 4;           // plus one helper warp per quarter
 constexpr int kNT = kNW * 32;
-constexpr int kTile = kRows * kR;      // 16384 outputs
-constexpr int kPitch = kR + 4;         // block pitch in shared memory (words)
+constexpr int kTile = kRows * kR;      // 12288 outputs
+constexpr int kPitch = kR + 4;         // block pitch in shared memory (words); 25 chunks: odd
 constexpr int kCols = 512;             // TMEM columns
 constexpr int kNearMax = kCols - kR;   // largest tap offset served from TMEM
-constexpr int kMaxBlocks = 156;        // 2 x 156 x 528 B + staging + program fits 227 KB
+constexpr int kRegsCompute = 144, kRegsHelper = 80;  // 12*32*144 + 4*32*80 == 65536
+constexpr int kBarBytes = 256;
 static_assert(kRG == 32, "a thread owns 32 outputs (two tcgen05.ld x16)");
+static_assert(kCW * 32 * kRegsCompute + 4 * 32 * kRegsHelper <= 65536, "register file");
+
+// mbarrier slots (uint64 each)
+enum { B_IN_FULL = 0, B_IN_FREE = 3, B_TM_FULL = 6, B_TM_FREE = 10, B_ST_FULL = 14, B_ST_FREE = 18, B_COUNT = 22 };
 
 // ---- tensor-memory primitives -------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc_all(uint32_t* slot) {
@@ -93,18 +106,41 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float4 (&v)[8]) 
       : "memory");
 }
 
-struct TmParams {
-  FirParams f;
-  int nblk;  // 128-sample blocks staged per tile (tile + halo)
-  int tiles_per_run;
-  int runs_per_channel;
-  long long n_runs;
-  long long tiles_per_channel;  // interior tiles
-};
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_u32(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_u32(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void set_max_regs_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void set_max_regs_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // ---- packed fp32 arithmetic (sm_100+): FADD2 / FMUL2 do two IEEE round-to-nearest operations per
-// instruction on an aligned register pair.  Same bits as two scalar operations, half the issue
-// slots — and issue slots, not the FP32 pipe, are what this kernel runs out of.
+// instruction on an aligned register pair.  Same bits as two scalar operations, half the issue slots.
 typedef unsigned long long pair_t;
 __device__ __forceinline__ pair_t pk(float a, float b) {
   pair_t r;
@@ -112,34 +148,37 @@ __device__ __forceinline__ pair_t pk(float a, float b) {
   return r;
 }
 __device__ __forceinline__ void upk(pair_t r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
-// In-place forms ("+l"): with a separate destination ptxas writes the result over the loaded operand
-// and copies it back into the accumulator pair (32 extra moves per tap).
 __device__ __forceinline__ pair_t add2(pair_t a, pair_t b) {
   asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
-  return a;
-}
-__device__ __forceinline__ pair_t sub2(pair_t a, pair_t b) {
-  asm("sub.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
   return a;
 }
 __device__ __forceinline__ pair_t mul2(pair_t a, pair_t b) {
   asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
   return a;
 }
-constexpr int kNP = kRG / 2;  // register pairs per thread
 
-__device__ __forceinline__ void bar_quarter(int q) { asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory"); }
+struct TmParams {
+  FirParams f;
+  int nblk;  // 96-sample blocks staged per tile (tile + halo)
+  int nbuf;  // tile buffers in shared memory (2 or 3)
+  int tiles_per_run;
+  int runs_per_channel;
+  int n_runs;
+  int tiles_per_channel;  // interior tiles
+};
 
 // The negative list is accumulated with adds and negated once at the end of the list:
 // fl(-a - b) == -fl(a + b) in round-to-nearest, and a zero of the other sign cannot survive into the
 // output (the running output is never -0).  One add body per datapath.
 
-// A tap served from tensor memory: acc += x[n + i] for the thread's 32 outputs.
-__device__ __forceinline__ void near_tap(uint32_t tcol, pair_t (&acc)[kNP]) {
-  float t[kRG];
+// A tap served from tensor memory is a 32-column load followed by 16 packed adds.  Loads are issued
+// one tap ahead into the other of two register buffers; tcgen05.wait::ld waits for every load in
+// flight, so the order is: wait for this tap's buffer, issue the next tap's load, then add.
+__device__ __forceinline__ void near_issue(float (&t)[kRG], uint32_t tcol) {
   tmem_ld16<0>(t, tcol);
   tmem_ld16<16>(t, tcol + 16);
-  tmem_wait_ld(t);
+}
+__device__ __forceinline__ void near_add(const float (&t)[kRG], pair_t (&acc)[kNP]) {
 #pragma unroll
   for (int j = 0; j < kNP; ++j) acc[j] = add2(acc[j], pk(t[2 * j], t[2 * j + 1]));
 }
@@ -147,34 +186,22 @@ __device__ __forceinline__ void near_tap(uint32_t tcol, pair_t (&acc)[kNP]) {
 // A tap served from shared memory.  `row` points at the staged block of this thread's row; `o` is
 // the offset of the thread's first operand relative to it (32 g + i); A = o & 3 is warp-uniform.
 // The 32 operands lie in 8 (A == 0) or 9 aligned 16-byte chunks; the run crosses at most one block
-// boundary, where the pitch inserts a 4-word gap: KX = chunks before the gap.
-template <int NC, int KX>
-__device__ __forceinline__ void far_load(const float4* __restrict__ p, float4 (&c)[NC]) {
-#pragma unroll
-  for (int k = 0; k < NC; ++k) c[k] = p[k + (k >= KX ? 1 : 0)];
-}
-
+// boundary, where the pitch inserts a 4-word gap after kx chunks.
 template <int A>
 __device__ __forceinline__ void far_tap_a(const float* __restrict__ row, int o, pair_t (&acc)[kNP]) {
   constexpr int NC = (A == 0) ? 8 : 9;
   const int oal = o - A;
-  const int w = oal & (kR - 1);
-  const float4* p = reinterpret_cast<const float4*>(row + (oal >> 7) * kPitch + w);
+  const int blk = oal / kR;
+  const int w = oal - blk * kR;
+  const float4* p = reinterpret_cast<const float4*>(row + blk * kPitch + w);
   const int kx = (kR - w) >> 2;  // >= 1
   float4 c[NC];
   if (kx >= NC) {
-    far_load<NC, NC>(p, c);
-  } else {  // static addressing per crossing position
-    switch (kx) {
-      case 1: far_load<NC, 1>(p, c); break;
-      case 2: far_load<NC, 2>(p, c); break;
-      case 3: far_load<NC, 3>(p, c); break;
-      case 4: far_load<NC, 4>(p, c); break;
-      case 5: far_load<NC, 5>(p, c); break;
-      case 6: far_load<NC, 6>(p, c); break;
-      case 7: far_load<NC, 7>(p, c); break;
-      default: far_load<NC, 8>(p, c); break;
-    }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) c[k] = p[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < NC; ++k) c[k] = (k < kx ? p : p + 1)[k];
   }
   float t[NC * 4];
 #pragma unroll
@@ -186,8 +213,7 @@ __device__ __forceinline__ void far_tap_a(const float* __restrict__ row, int o, 
   }
   if constexpr (A % 2 == 0) {  // operands arrive as aligned register pairs
 #pragma unroll
-    for (int j = 0; j < kNP; ++j)
-      acc[j] = add2(acc[j], pk(t[2 * j + A], t[2 * j + 1 + A]));
+    for (int j = 0; j < kNP; ++j) acc[j] = add2(acc[j], pk(t[2 * j + A], t[2 * j + 1 + A]));
   } else {  // odd shift: the pairs of the loaded data straddle the accumulator pairs -> scalar adds
 #pragma unroll
     for (int j = 0; j < kNP; ++j) {
@@ -209,174 +235,338 @@ __device__ __forceinline__ void far_tap(const float* __restrict__ row, int o, pa
   }
 }
 
-__device__ __forceinline__ void one_tap(int i, int og, uint32_t tcol0, const float* __restrict__ row, pair_t (&acc)[kNP]) {
-  if (i <= kNearMax) near_tap(tcol0 + (uint32_t)i, acc);
-  else far_tap(row, i + og, acc);
+constexpr int kNoTap = 0x7fffffff;
+
+// One tap whose TMEM load (if it is a near tap) is already in flight in `tx`; the next tap's load goes to `ty`.
+__device__ __forceinline__ void tap_step(int i, int i_next, float (&tx)[kRG], float (&ty)[kRG], int og, uint32_t tcol0,
+                                         const float* __restrict__ row, pair_t (&acc)[kNP]) {
+  if (i <= kNearMax) {
+    tmem_wait_ld(tx);
+    if (i_next <= kNearMax) near_issue(ty, tcol0 + (uint32_t)i_next);
+    near_add(tx, acc);
+  } else {  // no load in flight across a far tap: its 36 operand registers need the room
+    far_tap(row, i + og, acc);
+    if (i_next <= kNearMax) near_issue(ty, tcol0 + (uint32_t)i_next);
+  }
 }
 
-// Shared memory: [0,16) two mbarriers | [16,20) TMEM base | [64, ...) float in[2][nblk][132] |
-//                float stage[128][132] | int program[]
-__global__ void __launch_bounds__(kNT, 1) fir_tmem_kernel(const TmParams P) {
+__device__ __forceinline__ void negate(pair_t (&acc)[kNP]) {
+  const pair_t m1 = pk(-1.0f, -1.0f);
+#pragma unroll
+  for (int j = 0; j < kNP; ++j) acc[j] = mul2(acc[j], m1);
+}
+
+// Segments [s0, s1) of the program added into the running output, in the reference's order.
+// ALLFAR: none of these segments has a tap inside the TMEM window (no tensor-memory code at all).
+template <bool ALLFAR>
+__device__ __forceinline__ void run_segments(const int* __restrict__ sprog, int s0, int s1, const int*& tp, int apply_gain, int og,
+                                             uint32_t tcol0, const float* __restrict__ row, pair_t (&yv)[kNP]) {
+  const int* seg = sprog + 1;
+  for (int s = s0; s < s1; ++s) {
+    const int n_neg = seg[3 * s], n_tot = n_neg + seg[3 * s + 1];
+    pair_t acc[kNP];
+#pragma unroll
+    for (int j = 0; j < kNP; ++j) acc[j] = 0ull;
+    if constexpr (ALLFAR) {
+      int i_next = tp[0];  // one word of slack follows the program, so the prefetches stay in bounds
+      for (int k = 0; k < n_tot; ++k) {
+        const int i = i_next;
+        i_next = tp[k + 1];
+        far_tap(row, i + og, acc);
+        if (k + 1 == n_neg) negate(acc);  // end of the negative list: acc = -(sum of its taps)
+      }
+    } else if constexpr (!VND_TM_DOUBLE) {
+      int i_next = tp[0];
+      for (int k = 0; k < n_tot; ++k) {
+        const int i = i_next;
+        i_next = tp[k + 1];
+        if (i <= kNearMax) {
+          float t[kRG];
+          near_issue(t, tcol0 + (uint32_t)i);
+          tmem_wait_ld(t);
+          near_add(t, acc);
+        } else {
+          far_tap(row, i + og, acc);
+        }
+        if (k + 1 == n_neg) negate(acc);
+      }
+    } else {
+      float ta[kRG], tb[kRG];
+      int i0 = n_tot > 0 ? tp[0] : kNoTap;
+      if (i0 <= kNearMax) near_issue(ta, tcol0 + (uint32_t)i0);
+      for (int k = 0; k < n_tot; k += 2) {
+        const int i1 = (k + 1 < n_tot) ? tp[k + 1] : kNoTap;
+        tap_step(i0, i1, ta, tb, og, tcol0, row, acc);
+        if (k + 1 == n_neg) negate(acc);
+        if (k + 1 >= n_tot) break;
+        i0 = (k + 2 < n_tot) ? tp[k + 2] : kNoTap;
+        tap_step(i1, i0, tb, ta, og, tcol0, row, acc);
+        if (k + 2 == n_neg) negate(acc);
+      }
+    }
+    tp += n_tot;
+    if (apply_gain) {
+      const float gain = __int_as_float(seg[3 * s + 2]);
+      const pair_t g2 = pk(gain, gain);
+#pragma unroll
+      for (int j = 0; j < kNP; ++j) acc[j] = mul2(acc[j], g2);
+    }
+    if (s == 0) {
+#pragma unroll
+      for (int j = 0; j < kNP; ++j) yv[j] = add2(acc[j], 0ull);  // the reference adds into zeros
+    } else {
+#pragma unroll
+      for (int j = 0; j < kNP; ++j) yv[j] = add2(yv[j], acc[j]);
+    }
+  }
+}
+
+// Dynamic shared memory: [0,176) mbarriers | [192,196) TMEM base | [196,200) first all-far segment |
+//                        [256, ...) float in[nbuf][nblk][100] | float stage[128][100] | int program[]
+// The role functions rebuild their pointers from this symbol so that every access stays in the
+// shared address space (LDS/STS, not generic loads).
+extern __shared__ __align__(128) unsigned char tm_smem[];
+
+struct Smem {
+  uint64_t* bars;
+  int* s_near_end;
+  float* in_all;
+  float* stage;
+  int* sprog;
+  int bufw;
+  __device__ __forceinline__ explicit Smem(const TmParams& P) {
+    bars = reinterpret_cast<uint64_t*>(tm_smem);
+    s_near_end = reinterpret_cast<int*>(tm_smem + 196);
+    in_all = reinterpret_cast<float*>(tm_smem + kBarBytes);
+    bufw = P.nblk * kPitch;
+    stage = in_all + P.nbuf * bufw;
+    sprog = reinterpret_cast<int*>(stage + kRows * kPitch);
+  }
+};
+
+struct RunInfo {
+  int c, first_tile, n_tiles, nprog;
+};
+
+// Per-run prologue shared by both roles (every thread of the CTA takes part): decode the run, copy
+// the unfiltered channel through or load the channel's program.  Returns false for a copied run.
+__device__ __forceinline__ bool begin_run(const TmParams& P, const Smem& sm, int run, int tid, RunInfo& r) {
   const FirParams& p = P.f;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  uint32_t* tm_slot = reinterpret_cast<uint32_t*>(smem_raw + 16);
-  float* in_all = reinterpret_cast<float*>(smem_raw + 64);
-  const int bufw = P.nblk * kPitch;
-  float* stage = in_all + 2 * bufw;
-  int* sprog = reinterpret_cast<int*>(stage + kRows * kPitch);
+  r.c = run / P.runs_per_channel;
+  r.first_tile = (run % P.runs_per_channel) * P.tiles_per_run;
+  r.n_tiles = P.tiles_per_channel - r.first_tile;
+  if (r.n_tiles > P.tiles_per_run) r.n_tiles = P.tiles_per_run;
+  const int w0 = p.offsets[r.c];
+  r.nprog = p.offsets[r.c + 1] - w0;
+  if (r.nprog == 0) {  // unfiltered channel: copy through (decorrelation.py:399-400)
+    const float* xc = reinterpret_cast<const float*>(p.x) + (long long)r.c * p.x_sc;
+    float* yc = p.y + (long long)r.c * p.y_sc;
+    const long long t_begin = (long long)r.first_tile * kTile, t_end = t_begin + (long long)r.n_tiles * kTile;
+    for (long long t = t_begin + 4 * tid; t < t_end; t += 4 * kNT)
+      *reinterpret_cast<float4*>(yc + t) = *reinterpret_cast<const float4*>(xc + t);
+    return false;
+  }
+  __syncthreads();  // the pipeline of the previous run has drained: program and buffers are free
+  for (int i = tid; i < r.nprog; i += kNT) sm.sprog[i] = p.words[w0 + i];
+  if (tid == 0) sm.sprog[r.nprog] = 0;  // slack word read by the tap prefetch
+  __syncthreads();
+  if (tid == 0) {  // segments from this one on have no tap inside the TMEM window
+    const int S = sm.sprog[0];
+    const int* tq = sm.sprog + 1 + 3 * S;
+    int ne = 0;
+    for (int s = 0; s < S; ++s) {
+      const int n = sm.sprog[1 + 3 * s] + sm.sprog[2 + 3 * s];
+      for (int k = 0; k < n; ++k)
+        if (tq[k] <= kNearMax) ne = s + 1;
+      tq += n;
+    }
+    *sm.s_near_end = ne;
+  }
+  __syncthreads();
+  return true;
+}
+
+// ---------------------------------------------------------------- helper warp of lane quarter q
+__device__ __noinline__ void helper_main(const TmParams& P, uint32_t tbase, int tid) {
+  const Smem sm(P);
+  const int nbuf = P.nbuf, nblk = P.nblk, n_runs = P.n_runs;  // P lives behind a generic pointer here
+  const int lane = tid & 31, q = (tid >> 5) & 3;
+  const int m = 32 * q + lane;
+  // shared-memory addresses as 32-bit offsets: half the registers of generic pointers
+  const uint32_t bars = smem_u32(sm.bars), in0 = smem_u32(sm.in_all), buf_bytes = (uint32_t)sm.bufw * 4u;
+  const uint32_t stage_row = smem_u32(sm.stage + m * kPitch);
+  const uint32_t tx_bytes = (uint32_t)nblk * (kR * 4u);
+  // blocks k0 and k0 + 128 of every tile are loaded by this lane (block k -> helper k % 4)
+  const int k0 = q + 4 * lane;
+  const bool two = k0 + 128 < nblk;
+  // ring positions: fb/fpar follow the tile being filled, lb/lpar the tile being loaded
+  int fb = 0, lb = 0;
+  unsigned fpar = 0, lpar = 1;  // in_full parity of the next fill; in_free parity of the next load
+  unsigned tpar = 0;            // parity of the tile counter (TMEM and staging barriers)
+  for (int run = blockIdx.x; run < n_runs; run += gridDim.x) {
+    RunInfo r;
+    if (!begin_run(P, sm, run, tid, r)) continue;
+    const float* xnext = reinterpret_cast<const float*>(P.f.x) + (long long)r.c * P.f.x_sc + (long long)r.first_tile * kTile + k0 * kR;
+    float* ynext = P.f.y + (long long)r.c * P.f.y_sc + (long long)r.first_tile * kTile + m * kR;
+    int loads_left = r.n_tiles;
+    // ---- bulk loads of the next tile of the run into ring slot lb
+#define VND_ISSUE_LOAD()                                                                              \
+  do {                                                                                                \
+    mbar_wait_u32(bars + 8u * (B_IN_FREE + lb), lpar); /* every warp is done with the tile that was there */ \
+    const uint32_t full = bars + 8u * (B_IN_FULL + lb);                                               \
+    if (q == 0 && lane == 0) mbar_expect_tx_u32(full, tx_bytes);                                      \
+    const uint32_t dst = in0 + (uint32_t)lb * buf_bytes + (uint32_t)k0 * (kPitch * 4u);               \
+    fence_proxy_async();                                                                              \
+    if (k0 < nblk) bulk_g2s_u32(dst, xnext, kR * 4u, full);                                           \
+    if (two) bulk_g2s_u32(dst + 128u * (kPitch * 4u), xnext + 128 * kR, kR * 4u, full);               \
+    xnext += kTile;                                                                                   \
+    --loads_left;                                                                                     \
+    if (++lb == nbuf) {                                                                               \
+      lb = 0;                                                                                         \
+      lpar ^= 1u;                                                                                     \
+    }                                                                                                 \
+  } while (0)
+    for (int d = 0; d < nbuf - 1 && loads_left > 0; ++d) VND_ISSUE_LOAD();
+    for (int ti = 0; ti < r.n_tiles; ++ti) {
+      mbar_wait_u32(bars + 8u * (B_IN_FULL + fb), fpar);
+      mbar_wait_u32(bars + 8u * (B_TM_FREE + q), tpar ^ 1u);  // the quarter is past its last TMEM tap of the previous tile
+      tmem_fence_after();
+      {  // fill row m: 32 columns per step; a block of 96 samples is three steps, then the pitch skips 4 words
+        const float4* src = reinterpret_cast<const float4*>(sm.in_all + fb * sm.bufw + m * kPitch);
+        uint32_t tcol = tbase;
+        int sub = 0;
+#pragma unroll 1
+        for (int k32 = 0; k32 < kCols / 32; ++k32) {
+          float4 v[8];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) v[jj] = src[jj];
+          tmem_st32(tcol, v);
+          tcol += 32;
+          src += 8;
+          if (++sub == 3) {
+            sub = 0;
+            src += 1;
+          }
+        }
+        tmem_wait_st();
+      }
+      tmem_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_u32(bars + 8u * (B_TM_FULL + q));
+        mbar_arrive_u32(bars + 8u * (B_IN_FREE + fb));
+      }
+      if (++fb == nbuf) {
+        fb = 0;
+        fpar ^= 1u;
+      }
+      if (ti > 0) {  // the previous tile's rows of this quarter: one 384-byte store per lane
+        mbar_wait_u32(bars + 8u * (B_ST_FULL + q), tpar ^ 1u);
+        bulk_s2g_u32(ynext, stage_row, kR * 4u);
+        bulk_commit();
+        ynext += kTile;
+      }
+      if (loads_left > 0) VND_ISSUE_LOAD();
+      if (ti > 0) {
+        bulk_wait_read0();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_u32(bars + 8u * (B_ST_FREE + q));
+      }
+      tpar ^= 1u;
+    }
+#undef VND_ISSUE_LOAD
+    mbar_wait_u32(bars + 8u * (B_ST_FULL + q), tpar ^ 1u);
+    bulk_s2g_u32(ynext, stage_row, kR * 4u);
+    bulk_commit();
+    bulk_wait_read0();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_u32(bars + 8u * (B_ST_FREE + q));
+  }
+}
+
+// ---------------------------------------------------------------- compute warp (q, g)
+__device__ __noinline__ void compute_main(const TmParams& P, uint32_t tbase, int tid) {
+  const Smem sm(P);
+  const int nbuf = P.nbuf, n_runs = P.n_runs, apply_gain = P.f.apply_gain;  // P lives behind a generic pointer here
+  const int lane = tid & 31, warp = tid >> 5;
+  const int q = warp & 3, g = warp >> 2;
+  const int m = 32 * q + lane;
+  uint64_t* bars = sm.bars;
+  const uint32_t tcol0 = tbase + (uint32_t)(kRG * g);  // column of this thread's first output
+  int it = 0;
+  for (int run = blockIdx.x; run < n_runs; run += gridDim.x) {
+    RunInfo r;
+    if (!begin_run(P, sm, run, tid, r)) continue;
+    const int S = sm.sprog[0];
+    const int near_end = *sm.s_near_end;
+    for (int ti = 0; ti < r.n_tiles; ++ti) {
+      const int j = it + ti;
+      const int b = j % nbuf, u = j / nbuf;
+      const float* row = sm.in_all + b * sm.bufw + m * kPitch;
+      pair_t yv[kNP];
+#pragma unroll
+      for (int jj = 0; jj < kNP; ++jj) yv[jj] = 0ull;
+      const int* tp = sm.sprog + 1 + 3 * S;
+      mbar_wait(&bars[B_IN_FULL + b], u & 1);
+      mbar_wait(&bars[B_TM_FULL + q], j & 1);
+      tmem_fence_after();
+      run_segments<false>(sm.sprog, 0, near_end, tp, apply_gain, kRG * g, tcol0, row, yv);
+      tmem_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_TM_FREE + q]);  // the helper may fill TMEM for the next tile
+      run_segments<true>(sm.sprog, near_end, S, tp, apply_gain, kRG * g, tcol0, row, yv);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_IN_FREE + b]);
+      mbar_wait(&bars[B_ST_FREE + q], (j & 1) ^ 1);  // the previous tile's stores have read the staging rows
+      {
+        float4* dst = reinterpret_cast<float4*>(sm.stage + m * kPitch + kRG * g);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          float4 v;
+          upk(yv[2 * jj], v.x, v.y);
+          upk(yv[2 * jj + 1], v.z, v.w);
+          dst[jj] = v;
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_ST_FULL + q]);
+    }
+    it += r.n_tiles;
+  }
+}
+
+__global__ void __launch_bounds__(kNT, 1) fir_tmem_kernel(const __grid_constant__ TmParams P) {
+  const Smem sm(P);
+  uint32_t* tm_slot = reinterpret_cast<uint32_t*>(tm_smem + 192);
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, g = warp >> 2;
-  const int m = 32 * q + lane;  // this thread's row (TMEM lane)
-
+  const int warp = tid >> 5;
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    for (int b = 0; b < 3; ++b) {
+      mbar_init(&sm.bars[B_IN_FULL + b], 1);
+      mbar_init(&sm.bars[B_IN_FREE + b], kNW);
+    }
+    for (int k = 0; k < 4; ++k) {
+      mbar_init(&sm.bars[B_TM_FULL + k], 1);
+      mbar_init(&sm.bars[B_TM_FREE + k], kG);
+      mbar_init(&sm.bars[B_ST_FULL + k], kG);
+      mbar_init(&sm.bars[B_ST_FREE + k], 1);
+    }
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc_all(tm_slot);
   tmem_fence_before();
   __syncthreads();
   tmem_fence_after();
-  const uint32_t tbase = *tm_slot + ((uint32_t)(32 * q) << 16);
-  const uint32_t tcol0 = tbase + (uint32_t)(kRG * g);  // column of this thread's first output
-  unsigned phases = 0;  // bit b: parity of the next completion of tile buffer b
-  bool pending_store = false;
-
-  for (int run = blockIdx.x; run < (int)P.n_runs; run += gridDim.x) {
-    const int c = run / P.runs_per_channel;
-    const int first_tile = (run % P.runs_per_channel) * P.tiles_per_run;
-    int n_tiles = (int)P.tiles_per_channel - first_tile;
-    if (n_tiles > P.tiles_per_run) n_tiles = P.tiles_per_run;
-    const int w0 = p.offsets[c];
-    const int nprog = p.offsets[c + 1] - w0;
-
-    if (nprog == 0) {  // unfiltered channel: copy through (decorrelation.py:399-400)
-      const float* xc = reinterpret_cast<const float*>(p.x) + (long long)c * p.x_sc;
-      float* yc = p.y + (long long)c * p.y_sc;
-      const long long t_begin = (long long)first_tile * kTile, t_end = t_begin + (long long)n_tiles * kTile;
-      for (long long t = t_begin + 4 * tid; t < t_end; t += 4 * kNT)
-        *reinterpret_cast<float4*>(yc + t) = *reinterpret_cast<const float4*>(xc + t);
-      continue;
-    }
-
-    __syncthreads();  // everyone is done with the previous run's program
-    for (int i = tid; i < nprog; i += kNT) sprog[i] = p.words[w0 + i];
-    if (tid == 0) sprog[nprog] = 0;  // slack word read by the tap prefetch
-
-    // one 512-byte bulk copy per 128-sample block.  UBLKCP is issued lane by lane, so the blocks are
-    // dealt out to all warps (block b -> warp b % 16, lane b / 16): nine short issues per warp.
-    auto issue = [&](int ti, int buf) {
-      const float* src = reinterpret_cast<const float*>(p.x) + (long long)c * p.x_sc + (long long)(first_tile + ti) * kTile;
-      float* dst = in_all + buf * bufw;
-      if (tid == 0) mbar_expect_tx(&bars[buf], (uint32_t)P.nblk * (kR * 4u));
-      const int b = warp + kNW * lane;
-      if (b < P.nblk) {
-        fence_proxy_async();
-        bulk_g2s(dst + b * kPitch, src + b * kR, kR * 4u, &bars[buf]);
-      }
-    };
-    issue(0, 0);
-    __syncthreads();  // program visible
-    const int S = sprog[0];
-
-    for (int ti = 0; ti < n_tiles; ++ti) {
-      const int buf = ti & 1;
-      if (ti + 1 < n_tiles) issue(ti + 1, buf ^ 1);  // that buffer was released by the last barrier
-      mbar_wait(&bars[buf], (phases >> buf) & 1u);
-      phases ^= 1u << buf;
-      const float* in = in_all + buf * bufw;
-      const float* row = in + m * kPitch;
-
-      // ---- fill: columns [128 g, 128 g + 128) of row m are block m + g ----
-      {
-        const float4* src = reinterpret_cast<const float4*>(in + (m + g) * kPitch);
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          float4 v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = src[8 * k4 + j];
-          tmem_st32(tbase + (uint32_t)(kR * g + 32 * k4), v);
-        }
-        tmem_wait_st();
-      }
-      tmem_fence_before();
-      bar_quarter(q);  // TMEM lanes are private to a lane quarter: its four warps are the only users
-      tmem_fence_after();
-
-      // ---- taps, in the reference's order: per segment the negative list, then the positive ----
-      pair_t yv[kNP];
-      {
-        const int* seg = sprog + 1;
-        const int* tp = sprog + 1 + 3 * S;
-        for (int s = 0; s < S; ++s) {
-          const int n_neg = seg[3 * s], n_pos = seg[3 * s + 1];
-          pair_t acc[kNP];
-#pragma unroll
-          for (int j = 0; j < kNP; ++j) acc[j] = 0ull;
-          int i_next = tp[0];  // one word of slack follows the program, so the prefetches stay in bounds
-          const int n_tot = n_neg + n_pos;
-          for (int k = 0; k < n_tot; ++k) {
-            const int i = i_next;
-            i_next = tp[k + 1];
-            one_tap(i, kRG * g, tcol0, row, acc);
-            if (k + 1 == n_neg) {  // end of the negative list: acc = -(sum of its taps)
-              const pair_t m1 = pk(-1.0f, -1.0f);
-#pragma unroll
-              for (int j = 0; j < kNP; ++j) acc[j] = mul2(acc[j], m1);
-            }
-          }
-          tp += n_tot;
-          if (p.apply_gain) {
-            const float gain = __int_as_float(seg[3 * s + 2]);
-            const pair_t g2 = pk(gain, gain);
-#pragma unroll
-            for (int j = 0; j < kNP; ++j) acc[j] = mul2(acc[j], g2);
-          }
-          if (s == 0) {
-#pragma unroll
-            for (int j = 0; j < kNP; ++j) yv[j] = add2(acc[j], 0ull);  // the reference adds into zeros
-          } else {
-#pragma unroll
-            for (int j = 0; j < kNP; ++j) yv[j] = add2(yv[j], acc[j]);
-          }
-        }
-        if (S == 0) {
-#pragma unroll
-          for (int j = 0; j < kNP; ++j) yv[j] = 0ull;
-        }
-      }
-
-      // ---- output: staging rows at pitch 132, then one 512-byte bulk store per row ----
-      if (lane < 8 && pending_store) bulk_wait_read0();  // this warp's staging rows are free again
-      tmem_fence_before();
-      bar_quarter(q);  // every tcgen05.ld of this quarter is done (next fill), its staging rows are free
-      tmem_fence_after();
-      {
-        float4* dst = reinterpret_cast<float4*>(stage + m * kPitch + kRG * g);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 v;
-          upk(yv[2 * j], v.x, v.y);
-          upk(yv[2 * j + 1], v.z, v.w);
-          dst[j] = v;
-        }
-      }
-      fence_proxy_async();
-      bar_quarter(q);  // staging rows of this quarter are complete
-      if (lane < 8) {  // row 32 q + 8 g + lane: eight 512-byte stores per warp
-        const int sr = 32 * q + 8 * g + lane;
-        float* yt = p.y + (long long)c * p.y_sc + (long long)(first_tile + ti) * kTile;
-        bulk_s2g(yt + sr * kR, stage + sr * kPitch, kR * 4u);
-        bulk_commit();
-        pending_store = true;
-      }
-      __syncthreads();  // all reads of this tile buffer are done: it may be refilled
-    }
+  const uint32_t tbase = *tm_slot + ((uint32_t)(32 * (warp & 3)) << 16);
+  if (warp >= kCW) {
+    set_max_regs_dec<kRegsHelper>();
+    helper_main(P, tbase, tid);
+  } else {
+    set_max_regs_inc<kRegsCompute>();
+    compute_main(P, tbase, tid);
   }
-  if (lane < 8 && pending_store) bulk_wait_read0();  // shared memory must outlive the bulk reads
   tmem_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc_all(*tm_slot);
@@ -391,28 +581,35 @@ int fir_tmem_launch(const FirParams& f, int max_prog_words, cudaStream_t st, lon
   *frames_done = 0;
   if (!f.bulk_ok || f.x_st != 1 || f.y_st != 1) return VND_EUNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(f.y) % 16) != 0 || (f.y_sc % 4) != 0) return VND_EUNSUPPORTED;
-  const int nblk = kRows + (f.halo + 4 + kR - 1) / kR;
-  if (nblk > kMaxBlocks) return VND_EUNSUPPORTED;
+  int nblk = kRows + (f.halo + 4 + kR - 1) / kR;
+  if (nblk < kRows + 6) nblk = kRows + 6;  // the TMEM fill reads 512 columns of every row
+  const size_t fixed = kBarBytes + (size_t)kRows * kPitch * 4 + (size_t)(max_prog_words + 4) * 4;
+  const size_t per_buf = (size_t)nblk * kPitch * 4;
+  int nbuf = 3;
+  if (fixed + 3 * per_buf > (size_t)kMaxDynSmem) nbuf = 2;
+  if (fixed + nbuf * per_buf > (size_t)kMaxDynSmem) return VND_EUNSUPPORTED;
   if (f.frames < (long long)nblk * kR + 3LL * kTile) return VND_EUNSUPPORTED;  // fewer than four interior tiles
-  const size_t smem = 64 + (size_t)2 * nblk * kPitch * 4 + (size_t)kRows * kPitch * 4 + (size_t)(max_prog_words + 4) * 4;
-  if (smem > (size_t)kMaxDynSmem) return VND_EUNSUPPORTED;
+  const size_t smem = fixed + nbuf * per_buf;
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
   TmParams P{};
   P.f = f;
   P.nblk = nblk;
-  P.tiles_per_channel = (f.frames - (long long)nblk * kR) / kTile + 1;
-  P.tiles_per_run = (int)(P.tiles_per_channel < VND_TM_RUN ? P.tiles_per_channel : VND_TM_RUN);
-  P.runs_per_channel = (int)ceil_div<long long>(P.tiles_per_channel, P.tiles_per_run);
-  P.n_runs = (long long)P.runs_per_channel * f.channels;
+  P.nbuf = nbuf;
+  const long long tiles = (f.frames - (long long)nblk * kR) / kTile + 1;
+  if (tiles > 0x3fffffffLL / (f.channels > 0 ? f.channels : 1)) return VND_EUNSUPPORTED;
+  P.tiles_per_channel = (int)tiles;
+  P.tiles_per_run = (int)(tiles < VND_TM_RUN ? tiles : VND_TM_RUN);
+  P.runs_per_channel = (int)ceil_div<long long>(tiles, P.tiles_per_run);
+  P.n_runs = P.runs_per_channel * f.channels;
   VND_CUDA_OK(cudaFuncSetAttribute(fir_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  long long grid = di.sm_count;
+  int grid = di.sm_count;
   if (grid > P.n_runs) grid = P.n_runs;
   fir_tmem_kernel<<<(unsigned)grid, kNT, smem, st>>>(P);
   rc = after_launch("fir_tmem_kernel");
   if (rc) return rc;
-  *frames_done = P.tiles_per_channel * kTile;
+  *frames_done = tiles * kTile;
   return VND_OK;
 }
 
