@@ -148,13 +148,23 @@ __device__ __forceinline__ pair_t pk(float a, float b) {
   return r;
 }
 __device__ __forceinline__ void upk(pair_t r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
-__device__ __forceinline__ pair_t add2(pair_t a, pair_t b) {
-  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
-  return a;
+// (a0, a1) += (b0, b1) and (a0, a1) *= (b0, b1): the accumulators stay scalar float variables and are
+// packed around each instruction; ptxas then keeps every pair in one aligned register pair and the
+// packing costs nothing.  (Loop-carried 64-bit accumulators made it write half of the results over
+// the loaded operand and copy them back.)
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+  pair_t ra, rb;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(ra) : "l"(rb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(ra));
 }
-__device__ __forceinline__ pair_t mul2(pair_t a, pair_t b) {
-  asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
-  return a;
+__device__ __forceinline__ void mul2(float& a0, float& a1, float b0, float b1) {
+  pair_t ra, rb;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));
+  asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(ra) : "l"(rb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(ra));
 }
 
 struct TmParams {
@@ -175,12 +185,15 @@ struct TmParams {
 // one tap ahead into the other of two register buffers; tcgen05.wait::ld waits for every load in
 // flight, so the order is: wait for this tap's buffer, issue the next tap's load, then add.
 __device__ __forceinline__ void near_issue(float (&t)[kRG], uint32_t tcol) {
-  tmem_ld16<0>(t, tcol);
-  tmem_ld16<16>(t, tcol + 16);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : VND_O16(t, 0), VND_O16(t, 16)
+      : "r"(tcol));
 }
-__device__ __forceinline__ void near_add(const float (&t)[kRG], pair_t (&acc)[kNP]) {
+__device__ __forceinline__ void near_add(const float (&t)[kRG], float (&acc)[kRG]) {
 #pragma unroll
-  for (int j = 0; j < kNP; ++j) acc[j] = add2(acc[j], pk(t[2 * j], t[2 * j + 1]));
+  for (int j = 0; j < kNP; ++j) add2(acc[2 * j], acc[2 * j + 1], t[2 * j], t[2 * j + 1]);
 }
 
 // A tap served from shared memory.  `row` points at the staged block of this thread's row; `o` is
@@ -188,7 +201,7 @@ __device__ __forceinline__ void near_add(const float (&t)[kRG], pair_t (&acc)[kN
 // The 32 operands lie in 8 (A == 0) or 9 aligned 16-byte chunks; the run crosses at most one block
 // boundary, where the pitch inserts a 4-word gap after kx chunks.
 template <int A>
-__device__ __forceinline__ void far_tap_a(const float* __restrict__ row, int o, pair_t (&acc)[kNP]) {
+__device__ __forceinline__ void far_tap_a(const float* __restrict__ row, int o, float (&acc)[kRG]) {
   constexpr int NC = (A == 0) ? 8 : 9;
   const int oal = o - A;
   const int blk = oal / kR;
@@ -213,20 +226,14 @@ __device__ __forceinline__ void far_tap_a(const float* __restrict__ row, int o, 
   }
   if constexpr (A % 2 == 0) {  // operands arrive as aligned register pairs
 #pragma unroll
-    for (int j = 0; j < kNP; ++j) acc[j] = add2(acc[j], pk(t[2 * j + A], t[2 * j + 1 + A]));
+    for (int j = 0; j < kNP; ++j) add2(acc[2 * j], acc[2 * j + 1], t[2 * j + A], t[2 * j + 1 + A]);
   } else {  // odd shift: the pairs of the loaded data straddle the accumulator pairs -> scalar adds
 #pragma unroll
-    for (int j = 0; j < kNP; ++j) {
-      float a0, a1;
-      upk(acc[j], a0, a1);
-      a0 = fadd(a0, t[2 * j + A]);
-      a1 = fadd(a1, t[2 * j + 1 + A]);
-      acc[j] = pk(a0, a1);
-    }
+    for (int r = 0; r < kRG; ++r) acc[r] = fadd(acc[r], t[r + A]);
   }
 }
 
-__device__ __forceinline__ void far_tap(const float* __restrict__ row, int o, pair_t (&acc)[kNP]) {
+__device__ __forceinline__ void far_tap(const float* __restrict__ row, int o, float (&acc)[kRG]) {
   switch (o & 3) {
     case 0: far_tap_a<0>(row, o, acc); break;
     case 1: far_tap_a<1>(row, o, acc); break;
@@ -239,7 +246,7 @@ constexpr int kNoTap = 0x7fffffff;
 
 // One tap whose TMEM load (if it is a near tap) is already in flight in `tx`; the next tap's load goes to `ty`.
 __device__ __forceinline__ void tap_step(int i, int i_next, float (&tx)[kRG], float (&ty)[kRG], int og, uint32_t tcol0,
-                                         const float* __restrict__ row, pair_t (&acc)[kNP]) {
+                                         const float* __restrict__ row, float (&acc)[kRG]) {
   if (i <= kNearMax) {
     tmem_wait_ld(tx);
     if (i_next <= kNearMax) near_issue(ty, tcol0 + (uint32_t)i_next);
@@ -250,23 +257,22 @@ __device__ __forceinline__ void tap_step(int i, int i_next, float (&tx)[kRG], fl
   }
 }
 
-__device__ __forceinline__ void negate(pair_t (&acc)[kNP]) {
-  const pair_t m1 = pk(-1.0f, -1.0f);
+__device__ __forceinline__ void negate(float (&acc)[kRG]) {
 #pragma unroll
-  for (int j = 0; j < kNP; ++j) acc[j] = mul2(acc[j], m1);
+  for (int j = 0; j < kNP; ++j) mul2(acc[2 * j], acc[2 * j + 1], -1.0f, -1.0f);
 }
 
 // Segments [s0, s1) of the program added into the running output, in the reference's order.
 // ALLFAR: none of these segments has a tap inside the TMEM window (no tensor-memory code at all).
 template <bool ALLFAR>
 __device__ __forceinline__ void run_segments(const int* __restrict__ sprog, int s0, int s1, const int*& tp, int apply_gain, int og,
-                                             uint32_t tcol0, const float* __restrict__ row, pair_t (&yv)[kNP]) {
+                                             uint32_t tcol0, const float* __restrict__ row, float (&yv)[kRG]) {
   const int* seg = sprog + 1;
   for (int s = s0; s < s1; ++s) {
     const int n_neg = seg[3 * s], n_tot = n_neg + seg[3 * s + 1];
-    pair_t acc[kNP];
+    float acc[kRG];
 #pragma unroll
-    for (int j = 0; j < kNP; ++j) acc[j] = 0ull;
+    for (int r = 0; r < kRG; ++r) acc[r] = 0.0f;
     if constexpr (ALLFAR) {
       int i_next = tp[0];  // one word of slack follows the program, so the prefetches stay in bounds
       for (int k = 0; k < n_tot; ++k) {
@@ -307,16 +313,15 @@ __device__ __forceinline__ void run_segments(const int* __restrict__ sprog, int 
     tp += n_tot;
     if (apply_gain) {
       const float gain = __int_as_float(seg[3 * s + 2]);
-      const pair_t g2 = pk(gain, gain);
 #pragma unroll
-      for (int j = 0; j < kNP; ++j) acc[j] = mul2(acc[j], g2);
+      for (int j = 0; j < kNP; ++j) mul2(acc[2 * j], acc[2 * j + 1], gain, gain);
     }
     if (s == 0) {
 #pragma unroll
-      for (int j = 0; j < kNP; ++j) yv[j] = add2(acc[j], 0ull);  // the reference adds into zeros
+      for (int r = 0; r < kRG; ++r) yv[r] = fadd(acc[r], 0.0f);  // the reference adds into zeros
     } else {
 #pragma unroll
-      for (int j = 0; j < kNP; ++j) yv[j] = add2(yv[j], acc[j]);
+      for (int j = 0; j < kNP; ++j) add2(yv[2 * j], yv[2 * j + 1], acc[2 * j], acc[2 * j + 1]);
     }
   }
 }
@@ -503,9 +508,9 @@ __device__ __noinline__ void compute_main(const TmParams& P, uint32_t tbase, int
       const int j = it + ti;
       const int b = j % nbuf, u = j / nbuf;
       const float* row = sm.in_all + b * sm.bufw + m * kPitch;
-      pair_t yv[kNP];
+      float yv[kRG];
 #pragma unroll
-      for (int jj = 0; jj < kNP; ++jj) yv[jj] = 0ull;
+      for (int r = 0; r < kRG; ++r) yv[r] = 0.0f;
       const int* tp = sm.sprog + 1 + 3 * S;
       mbar_wait(&bars[B_IN_FULL + b], u & 1);
       mbar_wait(&bars[B_TM_FULL + q], j & 1);
@@ -522,10 +527,7 @@ __device__ __noinline__ void compute_main(const TmParams& P, uint32_t tbase, int
         float4* dst = reinterpret_cast<float4*>(sm.stage + m * kPitch + kRG * g);
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
-          float4 v;
-          upk(yv[2 * jj], v.x, v.y);
-          upk(yv[2 * jj + 1], v.z, v.w);
-          dst[jj] = v;
+          dst[jj] = make_float4(yv[4 * jj], yv[4 * jj + 1], yv[4 * jj + 2], yv[4 * jj + 3]);
         }
       }
       fence_proxy_async();
