@@ -36,9 +36,6 @@
 #include "vnd_common.cuh"
 #include "vnd_fir.cuh"
 
-#ifndef VND_TM_DOUBLE
-#define VND_TM_DOUBLE 0  // 1: tensor-memory loads issued one tap ahead into a second register buffer
-#endif
 #ifndef VND_TM_RUN
 #define VND_TM_RUN 64  // consecutive tiles of one channel per CTA run
 #endif
@@ -141,31 +138,21 @@ __device__ __forceinline__ void set_max_regs_dec() { asm volatile("setmaxnreg.de
 
 // ---- packed fp32 arithmetic (sm_100+): FADD2 / FMUL2 do two IEEE round-to-nearest operations per
 // instruction on an aligned register pair.  Same bits as two scalar operations, half the issue slots.
+// The accumulators stay scalar float variables and are packed around each instruction; ptxas then
+// keeps every pair in one aligned register pair and the packing costs nothing.  (Loop-carried
+// 64-bit accumulators made it write half of the results over the loaded operand and copy them back.)
 typedef unsigned long long pair_t;
-__device__ __forceinline__ pair_t pk(float a, float b) {
-  pair_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void upk(pair_t r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
-// (a0, a1) += (b0, b1) and (a0, a1) *= (b0, b1): the accumulators stay scalar float variables and are
-// packed around each instruction; ptxas then keeps every pair in one aligned register pair and the
-// packing costs nothing.  (Loop-carried 64-bit accumulators made it write half of the results over
-// the loaded operand and copy them back.)
-__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
-  pair_t ra, rb;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));
-  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(ra) : "l"(rb));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(ra));
-}
-__device__ __forceinline__ void mul2(float& a0, float& a1, float b0, float b1) {
-  pair_t ra, rb;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));
-  asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(ra) : "l"(rb));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(ra));
-}
+#define VND_PACKED_OP(name, op)                                                     \
+  __device__ __forceinline__ void name(float& a0, float& a1, float b0, float b1) { \
+    pair_t ra, rb;                                                                  \
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));                    \
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));                    \
+    asm(op ".rn.f32x2 %0, %0, %1;" : "+l"(ra) : "l"(rb));                          \
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(ra));                   \
+  }
+VND_PACKED_OP(add2, "add")
+VND_PACKED_OP(sub2, "sub")
+VND_PACKED_OP(mul2, "mul")
 
 struct TmParams {
   FirParams f;
@@ -177,13 +164,7 @@ struct TmParams {
   int tiles_per_channel;  // interior tiles
 };
 
-// The negative list is accumulated with adds and negated once at the end of the list:
-// fl(-a - b) == -fl(a + b) in round-to-nearest, and a zero of the other sign cannot survive into the
-// output (the running output is never -0).  One add body per datapath.
-
-// A tap served from tensor memory is a 32-column load followed by 16 packed adds.  Loads are issued
-// one tap ahead into the other of two register buffers; tcgen05.wait::ld waits for every load in
-// flight, so the order is: wait for this tap's buffer, issue the next tap's load, then add.
+// A tap served from tensor memory: one 32-column load, then 16 packed adds (or subtracts).
 __device__ __forceinline__ void near_issue(float (&t)[kRG], uint32_t tcol) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
@@ -191,16 +172,20 @@ __device__ __forceinline__ void near_issue(float (&t)[kRG], uint32_t tcol) {
       : VND_O16(t, 0), VND_O16(t, 16)
       : "r"(tcol));
 }
+template <bool SUB>
 __device__ __forceinline__ void near_add(const float (&t)[kRG], float (&acc)[kRG]) {
 #pragma unroll
-  for (int j = 0; j < kNP; ++j) add2(acc[2 * j], acc[2 * j + 1], t[2 * j], t[2 * j + 1]);
+  for (int j = 0; j < kNP; ++j) {
+    if constexpr (SUB) sub2(acc[2 * j], acc[2 * j + 1], t[2 * j], t[2 * j + 1]);
+    else add2(acc[2 * j], acc[2 * j + 1], t[2 * j], t[2 * j + 1]);
+  }
 }
 
 // A tap served from shared memory.  `row` points at the staged block of this thread's row; `o` is
 // the offset of the thread's first operand relative to it (32 g + i); A = o & 3 is warp-uniform.
 // The 32 operands lie in 8 (A == 0) or 9 aligned 16-byte chunks; the run crosses at most one block
 // boundary, where the pitch inserts a 4-word gap after kx chunks.
-template <int A>
+template <int A, bool SUB>
 __device__ __forceinline__ void far_tap_a(const float* __restrict__ row, int o, float (&acc)[kRG]) {
   constexpr int NC = (A == 0) ? 8 : 9;
   const int oal = o - A;
@@ -226,91 +211,61 @@ __device__ __forceinline__ void far_tap_a(const float* __restrict__ row, int o, 
   }
   if constexpr (A % 2 == 0) {  // operands arrive as aligned register pairs
 #pragma unroll
-    for (int j = 0; j < kNP; ++j) add2(acc[2 * j], acc[2 * j + 1], t[2 * j + A], t[2 * j + 1 + A]);
+    for (int j = 0; j < kNP; ++j) {
+      if constexpr (SUB) sub2(acc[2 * j], acc[2 * j + 1], t[2 * j + A], t[2 * j + 1 + A]);
+      else add2(acc[2 * j], acc[2 * j + 1], t[2 * j + A], t[2 * j + 1 + A]);
+    }
   } else {  // odd shift: the pairs of the loaded data straddle the accumulator pairs -> scalar adds
 #pragma unroll
-    for (int r = 0; r < kRG; ++r) acc[r] = fadd(acc[r], t[r + A]);
+    for (int r = 0; r < kRG; ++r) acc[r] = SUB ? fsub(acc[r], t[r + A]) : fadd(acc[r], t[r + A]);
   }
 }
 
+template <bool SUB>
 __device__ __forceinline__ void far_tap(const float* __restrict__ row, int o, float (&acc)[kRG]) {
   switch (o & 3) {
-    case 0: far_tap_a<0>(row, o, acc); break;
-    case 1: far_tap_a<1>(row, o, acc); break;
-    case 2: far_tap_a<2>(row, o, acc); break;
-    default: far_tap_a<3>(row, o, acc); break;
+    case 0: far_tap_a<0, SUB>(row, o, acc); break;
+    case 1: far_tap_a<1, SUB>(row, o, acc); break;
+    case 2: far_tap_a<2, SUB>(row, o, acc); break;
+    default: far_tap_a<3, SUB>(row, o, acc); break;
   }
 }
 
-constexpr int kNoTap = 0x7fffffff;
-
-// One tap whose TMEM load (if it is a near tap) is already in flight in `tx`; the next tap's load goes to `ty`.
-__device__ __forceinline__ void tap_step(int i, int i_next, float (&tx)[kRG], float (&ty)[kRG], int og, uint32_t tcol0,
-                                         const float* __restrict__ row, float (&acc)[kRG]) {
-  if (i <= kNearMax) {
-    tmem_wait_ld(tx);
-    if (i_next <= kNearMax) near_issue(ty, tcol0 + (uint32_t)i_next);
-    near_add(tx, acc);
-  } else {  // no load in flight across a far tap: its 36 operand registers need the room
-    far_tap(row, i + og, acc);
-    if (i_next <= kNearMax) near_issue(ty, tcol0 + (uint32_t)i_next);
+// One list of taps applied to acc: the negative impulses of a segment (SUB) or the positive ones.
+// ALLFAR: no tap of the list lies inside the TMEM window (no tensor-memory code at all).
+template <bool SUB, bool ALLFAR>
+__device__ __forceinline__ void tap_list(const int* __restrict__ tp, int n, int og, uint32_t tcol0, const float* __restrict__ row,
+                                         float (&acc)[kRG]) {
+  int i_next = tp[0];  // one word of slack follows the program, so the prefetch stays in bounds
+  for (int k = 0; k < n; ++k) {
+    const int i = i_next;
+    i_next = tp[k + 1];
+    if (!ALLFAR && i <= kNearMax) {
+      float t[kRG];
+      near_issue(t, tcol0 + (uint32_t)i);
+      tmem_wait_ld(t);
+      near_add<SUB>(t, acc);
+    } else {
+      far_tap<SUB>(row, i + og, acc);
+    }
   }
 }
 
-__device__ __forceinline__ void negate(float (&acc)[kRG]) {
-#pragma unroll
-  for (int j = 0; j < kNP; ++j) mul2(acc[2 * j], acc[2 * j + 1], -1.0f, -1.0f);
-}
-
-// Segments [s0, s1) of the program added into the running output, in the reference's order.
-// ALLFAR: none of these segments has a tap inside the TMEM window (no tensor-memory code at all).
+// Segments [s0, s1) of the program added into the running output, in the reference's order
+// (decorrelation.py:402-414): acc = 0; acc -= x[n + i] over the negative list; acc += x[n + i] over
+// the positive list; acc *= gain; y += acc.
 template <bool ALLFAR>
 __device__ __forceinline__ void run_segments(const int* __restrict__ sprog, int s0, int s1, const int*& tp, int apply_gain, int og,
                                              uint32_t tcol0, const float* __restrict__ row, float (&yv)[kRG]) {
   const int* seg = sprog + 1;
   for (int s = s0; s < s1; ++s) {
-    const int n_neg = seg[3 * s], n_tot = n_neg + seg[3 * s + 1];
+    const int n_neg = seg[3 * s], n_pos = seg[3 * s + 1];
     float acc[kRG];
 #pragma unroll
     for (int r = 0; r < kRG; ++r) acc[r] = 0.0f;
-    if constexpr (ALLFAR) {
-      int i_next = tp[0];  // one word of slack follows the program, so the prefetches stay in bounds
-      for (int k = 0; k < n_tot; ++k) {
-        const int i = i_next;
-        i_next = tp[k + 1];
-        far_tap(row, i + og, acc);
-        if (k + 1 == n_neg) negate(acc);  // end of the negative list: acc = -(sum of its taps)
-      }
-    } else if constexpr (!VND_TM_DOUBLE) {
-      int i_next = tp[0];
-      for (int k = 0; k < n_tot; ++k) {
-        const int i = i_next;
-        i_next = tp[k + 1];
-        if (i <= kNearMax) {
-          float t[kRG];
-          near_issue(t, tcol0 + (uint32_t)i);
-          tmem_wait_ld(t);
-          near_add(t, acc);
-        } else {
-          far_tap(row, i + og, acc);
-        }
-        if (k + 1 == n_neg) negate(acc);
-      }
-    } else {
-      float ta[kRG], tb[kRG];
-      int i0 = n_tot > 0 ? tp[0] : kNoTap;
-      if (i0 <= kNearMax) near_issue(ta, tcol0 + (uint32_t)i0);
-      for (int k = 0; k < n_tot; k += 2) {
-        const int i1 = (k + 1 < n_tot) ? tp[k + 1] : kNoTap;
-        tap_step(i0, i1, ta, tb, og, tcol0, row, acc);
-        if (k + 1 == n_neg) negate(acc);
-        if (k + 1 >= n_tot) break;
-        i0 = (k + 2 < n_tot) ? tp[k + 2] : kNoTap;
-        tap_step(i1, i0, tb, ta, og, tcol0, row, acc);
-        if (k + 2 == n_neg) negate(acc);
-      }
-    }
-    tp += n_tot;
+    tap_list<true, ALLFAR>(tp, n_neg, og, tcol0, row, acc);
+    tap_list<false, ALLFAR>(tp + n_neg, n_pos, og, tcol0, row, acc);
+    tp += n_neg + n_pos;
     if (apply_gain) {
       const float gain = __int_as_float(seg[3 * s + 2]);
 #pragma unroll
