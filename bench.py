@@ -297,10 +297,16 @@ def run_b200(args) -> None:
             traffic = tr["dram_bytes_per_sample"] * Cg * L
         except Exception:
             traffic = None
-    kernel_name = "fir_tile_kernel<float,SEGMENTED>" if os.environ.get("VND_DISABLE_WINDOW") == "1" else "fir_window_kernel<R=29,W=32> (register-window, persistent, TMA double-buffered)"
+    if os.environ.get("VND_DISABLE_TMEM") != "1":
+        kernel_name = ("fir_tmem_kernel (tensor-memory Hankel rows + tcgen05.ld gathers, FADD2, warp-specialized, TMA bulk copies); "
+                       "the last ~1.5 tiles of every channel run on fir_tile_kernel in a second launch inside the same step")
+    elif os.environ.get("VND_DISABLE_WINDOW") != "1":
+        kernel_name = "fir_window_kernel<R=29,W=32> (register-window, persistent, TMA double-buffered)"
+    else:
+        kernel_name = "fir_tile_kernel<float,SEGMENTED>"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": kernel_name, "kernel_ms": kernel_ms, "peak_source": peak_src,
-                "lsu_pipe_frac": None, "note": "HBM is not the binding resource: every (output, tap) pair moves 4 B from shared memory (128 B/clk/SM); ncu shows that pipe 75-88 % busy with DRAM at 22-25 %. See DESIGN.md section 4 and profiles/r01_summary.md"}
+                "note": "HBM is not the binding resource: every (output, tap) pair moves one word from on-chip memory to a register and costs one add; the kernel is bound by instruction issue and on-chip latency (ncu: issue slots ~56 % busy, shared-memory pipe ~32 %, DRAM ~17 %). See DESIGN.md section 4 and profiles/r01_summary.md"}
 
     # end to end through the C ABI with HOST buffers (copies inside the timed region)
     e2e = None
