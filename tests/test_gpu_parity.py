@@ -257,8 +257,9 @@ def test_planar_slab_filter_shapes(api, kappa, envelope):
 @pytest.mark.parametrize(
     "frames,kappa,envelope,duration",
     [
-        (140 * 128 + 3 * 16384, 1.0, (0.85, 0.55, 0.35, 0.2), 0.03),  # the shortest slab the kernel takes: 4 interior tiles
-        (140 * 128 + 3 * 16384 + 1, 1.0, (0.85, 0.55, 0.35, 0.2), 0.03),
+        (-1, 1.0, (0.85, 0.55, 0.35, 0.2), 0.03),  # one frame short of the shortest slab the kernel takes (window kernel instead)
+        (0, 1.0, (0.85, 0.55, 0.35, 0.2), 0.03),  # the shortest slab it takes: 4 interior tiles, tail of exactly the halo blocks
+        (1, 1.0, (0.85, 0.55, 0.35, 0.2), 0.03),
         (200003, 0.0, (0.85, 0.55, 0.35, 0.2), 0.03),  # uniform impulses: most taps beyond the TMEM window
         (150000, 0.4, (1.0,), 0.03),  # identity envelope (no gain multiply), one segment
         (131072 + 9000, 1.0, (0.9, -0.5), 0.03),
@@ -275,6 +276,9 @@ def test_planar_slab_tmem_kernel(api, frames, kappa, envelope, duration):
     filtered = (0, 1, 2, 3)  # channel 4 is copied through
     vn = api.VelvetNoise(sample_rate_hz=48000, duration_seconds=duration, num_impulses=30, num_outs=C, filtered_channels=filtered,
                          mode="LR", normalizer=None, log_distribution_strength=kappa, segment_envelope=envelope, seed=5)
+    if frames <= 1:  # relative to the kernel's minimum: (128 + halo blocks) x 96 samples staged per tile + 3 more tiles of 12288
+        halo = vn.tap_program(1 << 20).halo
+        frames += (128 + -(-(halo + 4) // 96)) * 96 + 3 * 12288
     g = torch.Generator(device="cuda").manual_seed(99)
     slab = torch.randn((C, frames), generator=g, device="cuda") * 0.1
     slab[1, 20000:26000] = 0.0

@@ -20,18 +20,25 @@
 // taps of BASELINE config 3 qualify.  The remaining (far) taps read the staged tile from shared
 // memory with 16-byte loads.  Shared memory holds the tile as 96-sample blocks at a pitch of 100
 // words, so that lanes (rows) hit distinct bank groups with LDS.128 / STS.128: one 384-byte TMA
-// bulk copy per block.
+// row, three tile buffers.
 //
 // Roles (one CTA of 16 warps per SM; warp w works on TMEM lane quarter w & 3, which is also its
-// scheduler).  Warps 0-11 compute (setmaxnreg 152).  Warps 12-15, one per quarter, are helpers
-// (setmaxnreg 56): they issue the bulk loads, fill TMEM for the next tile (LDS.128 ->
-// tcgen05.st) as soon as the quarter's compute warps are past their last TMEM tap — i.e. while
-// those warps run the trailing all-far segments and stage their outputs — and issue the bulk
-// stores.  Everything is handed over through mbarriers; there is no CTA-wide barrier inside a run.
+// scheduler).  Warps 0-11 compute (setmaxnreg 144).  Warps 12-15, one per quarter (setmaxnreg 80),
+// move data: they refill the quarter's TMEM rows with the next tile (LDS.128 -> tcgen05.st) as soon
+// as the quarter's compute warps are past their last tensor-memory tap — i.e. while those warps run
+// the trailing all-far segments and stage their outputs — and issue the TMA requests: ONE tensor
+// load per tile, two tiles ahead (a 100 x nblk box over x seen as rows of 96 samples: the four
+// out-of-bounds columns are zero-filled, which produces the 100-word pitch), and one tensor store per
+// quarter and tile (the same trick clips the pad columns).  Hand-overs go through mbarriers; there
+// is no CTA-wide barrier inside a run.  The data-movement lanes sleep between mbarrier polls so that
+// polling does not take issue slots from the compute warps.
 //
 // The kernel only runs interior tiles (tile + halo completely inside the signal); the launcher
 // reports how many frames it covered and the caller finishes the tail of every channel with the
 // general tile kernel.
+
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+#include <stdlib.h>
 
 #include "vnd_common.cuh"
 #include "vnd_fir.cuh"
@@ -50,19 +57,21 @@ constexpr int kG = 3;                  // compute warps per lane quarter
 constexpr int kRG = kR / kG;           // outputs per thread
 constexpr int kNP = kRG / 2;           // register pairs per thread
 constexpr int kCW = 4 * kG;            // compute warps (warp w: lane quarter w & 3, group w >> 2)
-constexpr int kNW = kCW + 4;           // plus one helper warp per quarter
+constexpr int kNW = kCW + 4;           // plus one data-movement warp per quarter
 constexpr int kNT = kNW * 32;
 constexpr int kTile = kRows * kR;      // 12288 outputs
-constexpr int kPitch = kR + 4;         // block pitch in shared memory (words); 25 chunks: odd
+constexpr int kPitch = kR + 4;         // row pitch in shared memory (words); 25 chunks: odd
 constexpr int kCols = 512;             // TMEM columns
+constexpr int kUnits = kCols / 32;     // 32-column units of a TMEM row
 constexpr int kNearMax = kCols - kR;   // largest tap offset served from TMEM
+constexpr int kNBuf = 3;               // tile buffers in shared memory
 constexpr int kRegsCompute = 144, kRegsHelper = 80;  // 12*32*144 + 4*32*80 == 65536
 constexpr int kBarBytes = 256;
-static_assert(kRG == 32, "a thread owns 32 outputs (two tcgen05.ld x16)");
+static_assert(kRG == 32, "a thread owns 32 outputs (one 32-column tcgen05.ld)");
 static_assert(kCW * 32 * kRegsCompute + 4 * 32 * kRegsHelper <= 65536, "register file");
 
 // mbarrier slots (uint64 each)
-enum { B_IN_FULL = 0, B_IN_FREE = 3, B_TM_FULL = 6, B_TM_FREE = 10, B_ST_FULL = 14, B_ST_FREE = 18, B_COUNT = 22 };
+enum { B_IN_FULL = 0, B_IN_FREE = 3, B_ST_FULL = 6, B_ST_FREE = 10, B_TM_FULL = 14, B_TM_FREE = 18, B_COUNT = 22 };
 
 // ---- tensor-memory primitives -------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc_all(uint32_t* slot) {
@@ -110,6 +119,8 @@ __device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) { asm volatile("mb
 __device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// The data-movement lanes wait for whole tiles: they sleep between polls instead of spinning, so the
+// polling does not take issue slots from the compute warps of the same scheduler.
 __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -117,19 +128,22 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
       "WAIT_%=:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra DONE_%=;\n"
+      "nanosleep.u32 200;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
       "}\n" ::"r"(bar),
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void bulk_g2s_u32(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
-               "r"(bar)
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void bulk_s2g_u32(void* dst, uint32_t src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+__device__ __forceinline__ void tma_store_3d(const void* tmap, int c0, int c1, int c2, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2),
+               "r"(src)
+               : "memory");
 }
 template <int N>
 __device__ __forceinline__ void set_max_regs_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -155,9 +169,14 @@ VND_PACKED_OP(sub2, "sub")
 VND_PACKED_OP(mul2, "mul")
 
 struct TmParams {
+  // TMA descriptors of x and y seen as (96 samples, rows, channels).  The boxes are 100 wide: the four
+  // out-of-bounds elements per row are zero-filled on load and clipped on store, which gives the
+  // 100-word row pitch in shared memory with ONE request per tile instead of one per row.
+  alignas(64) CUtensorMap tmx;
+  alignas(64) CUtensorMap tmy;
   FirParams f;
-  int nblk;  // 96-sample blocks staged per tile (tile + halo)
-  int nbuf;  // tile buffers in shared memory (2 or 3)
+  int nblk;      // 96-sample blocks staged per tile (tile + halo)
+  int opstride;  // words reserved for the program and for each decoded list
   int tiles_per_run;
   int runs_per_channel;
   int n_runs;
@@ -181,18 +200,16 @@ __device__ __forceinline__ void near_add(const float (&t)[kRG], float (&acc)[kRG
   }
 }
 
-// A tap served from shared memory.  `row` points at the staged block of this thread's row; `o` is
-// the offset of the thread's first operand relative to it (32 g + i); A = o & 3 is warp-uniform.
-// The 32 operands lie in 8 (A == 0) or 9 aligned 16-byte chunks; the run crosses at most one block
-// boundary, where the pitch inserts a 4-word gap after kx chunks.
+// A tap served from shared memory.  `row` points at the staged block of this thread's row.  The
+// operation word (build_ops) carries the word offset of the aligned 16-byte chunk that holds the
+// thread's first operand, the operand's position A inside it and kx, the number of chunks before the
+// run crosses into the next block, where the pitch inserts a 4-word gap (kx >= 9: no crossing).
+// The 32 operands lie in 8 (A == 0) or 9 chunks.
 template <int A, bool SUB>
-__device__ __forceinline__ void far_tap_a(const float* __restrict__ row, int o, float (&acc)[kRG]) {
+__device__ __forceinline__ void far_tap_a(const float* __restrict__ row, int op, float (&acc)[kRG]) {
   constexpr int NC = (A == 0) ? 8 : 9;
-  const int oal = o - A;
-  const int blk = oal / kR;
-  const int w = oal - blk * kR;
-  const float4* p = reinterpret_cast<const float4*>(row + blk * kPitch + w);
-  const int kx = (kR - w) >> 2;  // >= 1
+  const float4* p = reinterpret_cast<const float4*>(row + (op & 0xffff));
+  const int kx = (op >> 16) & 15;
   float4 c[NC];
   if (kx >= NC) {
 #pragma unroll
@@ -221,33 +238,51 @@ __device__ __forceinline__ void far_tap_a(const float* __restrict__ row, int o, 
   }
 }
 
+// Tap operations, decoded once per run for each of the three thread groups (begin_run):
+//   near tap: the tap offset i itself (>= 0): the TMEM column is tcol0 + i
+//   far tap:  kOpFar | A << 24 | kx << 16 | word offset of the first chunk relative to the thread's row
+constexpr int kOpFar = (int)0x80000000u;
+
 template <bool SUB>
-__device__ __forceinline__ void far_tap(const float* __restrict__ row, int o, float (&acc)[kRG]) {
-  switch (o & 3) {
-    case 0: far_tap_a<0, SUB>(row, o, acc); break;
-    case 1: far_tap_a<1, SUB>(row, o, acc); break;
-    case 2: far_tap_a<2, SUB>(row, o, acc); break;
-    default: far_tap_a<3, SUB>(row, o, acc); break;
+__device__ __forceinline__ void far_tap(const float* __restrict__ row, int op, float (&acc)[kRG]) {
+  switch ((op >> 24) & 3) {
+    case 0: far_tap_a<0, SUB>(row, op, acc); break;
+    case 1: far_tap_a<1, SUB>(row, op, acc); break;
+    case 2: far_tap_a<2, SUB>(row, op, acc); break;
+    default: far_tap_a<3, SUB>(row, op, acc); break;
+  }
+}
+
+// One tap: from tensor memory (op >= 0) or from shared memory.
+template <bool SUB, bool ALLFAR>
+__device__ __forceinline__ void one_tap(int op, uint32_t tcol0, const float* __restrict__ row, float (&acc)[kRG]) {
+  if (!ALLFAR && op >= 0) {
+    float t[kRG];
+    near_issue(t, tcol0 + (uint32_t)op);
+    tmem_wait_ld(t);
+    near_add<SUB>(t, acc);
+  } else {
+    far_tap<SUB>(row, op, acc);
   }
 }
 
 // One list of taps applied to acc: the negative impulses of a segment (SUB) or the positive ones.
 // ALLFAR: no tap of the list lies inside the TMEM window (no tensor-memory code at all).
+// The loop is unrolled by two with the operation words in alternating registers, so that each word
+// is loaded a whole tap before it is needed and never copied (a single loop-carried register made
+// ptxas copy the loaded word at once and stall on the shared-memory latency at every tap).
 template <bool SUB, bool ALLFAR>
-__device__ __forceinline__ void tap_list(const int* __restrict__ tp, int n, int og, uint32_t tcol0, const float* __restrict__ row,
+__device__ __forceinline__ void tap_list(const int* __restrict__ ops, int n, uint32_t tcol0, const float* __restrict__ row,
                                          float (&acc)[kRG]) {
-  int i_next = tp[0];  // one word of slack follows the program, so the prefetch stays in bounds
-  for (int k = 0; k < n; ++k) {
-    const int i = i_next;
-    i_next = tp[k + 1];
-    if (!ALLFAR && i <= kNearMax) {
-      float t[kRG];
-      near_issue(t, tcol0 + (uint32_t)i);
-      tmem_wait_ld(t);
-      near_add<SUB>(t, acc);
-    } else {
-      far_tap<SUB>(row, i + og, acc);
-    }
+  if (n <= 0) return;
+  int op_a = ops[0];
+  for (int k = 0;; k += 2) {
+    const int op_b = ops[k + 1];  // two words of slack follow the lists, so the prefetches stay in bounds
+    one_tap<SUB, ALLFAR>(op_a, tcol0, row, acc);
+    if (k + 1 >= n) break;
+    op_a = ops[k + 2];
+    one_tap<SUB, ALLFAR>(op_b, tcol0, row, acc);
+    if (k + 2 >= n) break;
   }
 }
 
@@ -255,7 +290,7 @@ __device__ __forceinline__ void tap_list(const int* __restrict__ tp, int n, int 
 // (decorrelation.py:402-414): acc = 0; acc -= x[n + i] over the negative list; acc += x[n + i] over
 // the positive list; acc *= gain; y += acc.
 template <bool ALLFAR>
-__device__ __forceinline__ void run_segments(const int* __restrict__ sprog, int s0, int s1, const int*& tp, int apply_gain, int og,
+__device__ __forceinline__ void run_segments(const int* __restrict__ sprog, int s0, int s1, const int*& ops, int apply_gain,
                                              uint32_t tcol0, const float* __restrict__ row, float (&yv)[kRG]) {
   const int* seg = sprog + 1;
   for (int s = s0; s < s1; ++s) {
@@ -263,9 +298,9 @@ __device__ __forceinline__ void run_segments(const int* __restrict__ sprog, int 
     float acc[kRG];
 #pragma unroll
     for (int r = 0; r < kRG; ++r) acc[r] = 0.0f;
-    tap_list<true, ALLFAR>(tp, n_neg, og, tcol0, row, acc);
-    tap_list<false, ALLFAR>(tp + n_neg, n_pos, og, tcol0, row, acc);
-    tp += n_neg + n_pos;
+    tap_list<true, ALLFAR>(ops, n_neg, tcol0, row, acc);
+    tap_list<false, ALLFAR>(ops + n_neg, n_pos, tcol0, row, acc);
+    ops += n_neg + n_pos;
     if (apply_gain) {
       const float gain = __int_as_float(seg[3 * s + 2]);
 #pragma unroll
@@ -281,8 +316,8 @@ __device__ __forceinline__ void run_segments(const int* __restrict__ sprog, int 
   }
 }
 
-// Dynamic shared memory: [0,176) mbarriers | [192,196) TMEM base | [196,200) first all-far segment |
-//                        [256, ...) float in[nbuf][nblk][100] | float stage[128][100] | int program[]
+// Dynamic shared memory: [0,112) mbarriers | [192,196) TMEM base | [196,200) first all-far segment |
+//   [256, ...) float in[3][nblk][100] | float stage[128][100] | int program[] | int ops[3][]
 // The role functions rebuild their pointers from this symbol so that every access stays in the
 // shared address space (LDS/STS, not generic loads).
 extern __shared__ __align__(128) unsigned char tm_smem[];
@@ -293,14 +328,18 @@ struct Smem {
   float* in_all;
   float* stage;
   int* sprog;
+  int* ops;  // [3][opstride]: decoded tap operations per thread group
   int bufw;
+  int opstride;
   __device__ __forceinline__ explicit Smem(const TmParams& P) {
     bars = reinterpret_cast<uint64_t*>(tm_smem);
     s_near_end = reinterpret_cast<int*>(tm_smem + 196);
     in_all = reinterpret_cast<float*>(tm_smem + kBarBytes);
-    bufw = P.nblk * kPitch;
-    stage = in_all + P.nbuf * bufw;
+    bufw = (P.nblk * kPitch + 31) & ~31;  // TMA tensor copies want 128-byte aligned shared-memory addresses
+    stage = in_all + kNBuf * bufw;
     sprog = reinterpret_cast<int*>(stage + kRows * kPitch);
+    opstride = P.opstride;
+    ops = sprog + opstride;
   }
 };
 
@@ -309,7 +348,8 @@ struct RunInfo {
 };
 
 // Per-run prologue shared by both roles (every thread of the CTA takes part): decode the run, copy
-// the unfiltered channel through or load the channel's program.  Returns false for a copied run.
+// the unfiltered channel through or load and decode the channel's program.  Returns false for a
+// copied run.
 __device__ __forceinline__ bool begin_run(const TmParams& P, const Smem& sm, int run, int tid, RunInfo& r) {
   const FirParams& p = P.f;
   r.c = run / P.runs_per_channel;
@@ -326,13 +366,14 @@ __device__ __forceinline__ bool begin_run(const TmParams& P, const Smem& sm, int
       *reinterpret_cast<float4*>(yc + t) = *reinterpret_cast<const float4*>(xc + t);
     return false;
   }
-  __syncthreads();  // the pipeline of the previous run has drained: program and buffers are free
+  __syncthreads();  // the pipeline of the previous run has drained: program, buffers and TMEM are free
   for (int i = tid; i < r.nprog; i += kNT) sm.sprog[i] = p.words[w0 + i];
-  if (tid == 0) sm.sprog[r.nprog] = 0;  // slack word read by the tap prefetch
   __syncthreads();
+  const int S = sm.sprog[0];
+  const int* taps = sm.sprog + 1 + 3 * S;
+  const int ntaps = r.nprog - 1 - 3 * S;
   if (tid == 0) {  // segments from this one on have no tap inside the TMEM window
-    const int S = sm.sprog[0];
-    const int* tq = sm.sprog + 1 + 3 * S;
+    const int* tq = taps;
     int ne = 0;
     for (int s = 0; s < S; ++s) {
       const int n = sm.sprog[1 + 3 * s] + sm.sprog[2 + 3 * s];
@@ -342,51 +383,68 @@ __device__ __forceinline__ bool begin_run(const TmParams& P, const Smem& sm, int
     }
     *sm.s_near_end = ne;
   }
+  // decode the taps for the three thread groups (group g owns outputs 32 g .. 32 g + 31 of a row)
+  for (int t = tid; t < kG * (ntaps + 2); t += kNT) {
+    const int g = t / (ntaps + 2), k = t - g * (ntaps + 2);
+    int op = 0;  // two slack words behind each list
+    if (k < ntaps) {
+      const int i = taps[k];
+      if (i <= kNearMax) {
+        op = i;
+      } else {
+        const int o = i + kRG * g, A = o & 3, oal = o - A;
+        const int blk = oal / kR, w = oal - blk * kR;
+        int kx = (kR - w) >> 2;
+        if (kx > 9) kx = 9;
+        op = kOpFar | (A << 24) | (kx << 16) | (blk * kPitch + w);
+      }
+    }
+    sm.ops[g * sm.opstride + k] = op;
+  }
   __syncthreads();
   return true;
 }
 
-// ---------------------------------------------------------------- helper warp of lane quarter q
+// ---------------------------------------------------------------- data-movement warp of lane quarter q
+// One elected lane per warp: quarter 0 issues the tile loads (one TMA request per tile, three tiles
+// ahead), every quarter stores its own 32 staged rows (one request per tile).
 __device__ __noinline__ void helper_main(const TmParams& P, uint32_t tbase, int tid) {
   const Smem sm(P);
-  const int nbuf = P.nbuf, nblk = P.nblk, n_runs = P.n_runs;  // P lives behind a generic pointer here
+  const int nblk = P.nblk, n_runs = P.n_runs;  // P lives behind a generic pointer here
   const int lane = tid & 31, q = (tid >> 5) & 3;
   const int m = 32 * q + lane;
-  // shared-memory addresses as 32-bit offsets: half the registers of generic pointers
   const uint32_t bars = smem_u32(sm.bars), in0 = smem_u32(sm.in_all), buf_bytes = (uint32_t)sm.bufw * 4u;
-  const uint32_t stage_row = smem_u32(sm.stage + m * kPitch);
-  const uint32_t tx_bytes = (uint32_t)nblk * (kR * 4u);
-  // blocks k0 and k0 + 128 of every tile are loaded by this lane (block k -> helper k % 4)
-  const int k0 = q + 4 * lane;
-  const bool two = k0 + 128 < nblk;
-  // ring positions: fb/fpar follow the tile being filled, lb/lpar the tile being loaded
-  int fb = 0, lb = 0;
-  unsigned fpar = 0, lpar = 1;  // in_full parity of the next fill; in_free parity of the next load
-  unsigned tpar = 0;            // parity of the tile counter (TMEM and staging barriers)
+  const uint32_t stage_q = smem_u32(sm.stage + 32 * q * kPitch);
+  const uint32_t tx_bytes = (uint32_t)nblk * (kPitch * 4u);  // the whole box counts, zero-filled columns included
+  const void* tmx = &P.tmx;
+  const void* tmy = &P.tmy;
+  const bool loader = q == 0 && lane == 0;
+  int fb = 0, lb = 0;          // ring slots of the next fill and of the next load
+  unsigned fpar = 0, lpar = 1; // in_full parity of the next fill; in_free parity that releases slot lb
+  unsigned tpar = 0;           // parity of the tile counter (TMEM and staging barriers)
   for (int run = blockIdx.x; run < n_runs; run += gridDim.x) {
     RunInfo r;
     if (!begin_run(P, sm, run, tid, r)) continue;
-    const float* xnext = reinterpret_cast<const float*>(P.f.x) + (long long)r.c * P.f.x_sc + (long long)r.first_tile * kTile + k0 * kR;
-    float* ynext = P.f.y + (long long)r.c * P.f.y_sc + (long long)r.first_tile * kTile + m * kR;
-    int loads_left = r.n_tiles;
-    // ---- bulk loads of the next tile of the run into ring slot lb
-#define VND_ISSUE_LOAD()                                                                              \
-  do {                                                                                                \
-    mbar_wait_u32(bars + 8u * (B_IN_FREE + lb), lpar); /* every warp is done with the tile that was there */ \
-    const uint32_t full = bars + 8u * (B_IN_FULL + lb);                                               \
-    if (q == 0 && lane == 0) mbar_expect_tx_u32(full, tx_bytes);                                      \
-    const uint32_t dst = in0 + (uint32_t)lb * buf_bytes + (uint32_t)k0 * (kPitch * 4u);               \
-    fence_proxy_async();                                                                              \
-    if (k0 < nblk) bulk_g2s_u32(dst, xnext, kR * 4u, full);                                           \
-    if (two) bulk_g2s_u32(dst + 128u * (kPitch * 4u), xnext + 128 * kR, kR * 4u, full);               \
-    xnext += kTile;                                                                                   \
-    --loads_left;                                                                                     \
-    if (++lb == nbuf) {                                                                               \
-      lb = 0;                                                                                         \
-      lpar ^= 1u;                                                                                     \
-    }                                                                                                 \
+    int load_row = r.first_tile * kRows;  // first row (96 samples) of the next tile to load
+    int store_row = r.first_tile * kRows + 32 * q;
+    int to_load = r.n_tiles;
+#define VND_ISSUE_LOAD()                                                                   \
+  do {                                                                                     \
+    if (loader) {                                                                          \
+      mbar_wait_u32(bars + 8u * (B_IN_FREE + lb), lpar); /* every warp is done with the tile that was there */ \
+      const uint32_t full = bars + 8u * (B_IN_FULL + lb);                                  \
+      mbar_expect_tx_u32(full, tx_bytes);                                                  \
+      fence_proxy_async();                                                                 \
+      tma_load_3d(in0 + (uint32_t)lb * buf_bytes, tmx, 0, load_row, r.c, full);            \
+    }                                                                                      \
+    load_row += kRows;                                                                     \
+    --to_load;                                                                             \
+    if (++lb == kNBuf) {                                                                   \
+      lb = 0;                                                                              \
+      lpar ^= 1u;                                                                          \
+    }                                                                                      \
   } while (0)
-    for (int d = 0; d < nbuf - 1 && loads_left > 0; ++d) VND_ISSUE_LOAD();
+    for (int d = 0; d < kNBuf - 1 && to_load > 0; ++d) VND_ISSUE_LOAD();
     for (int ti = 0; ti < r.n_tiles; ++ti) {
       mbar_wait_u32(bars + 8u * (B_IN_FULL + fb), fpar);
       mbar_wait_u32(bars + 8u * (B_TM_FREE + q), tpar ^ 1u);  // the quarter is past its last TMEM tap of the previous tile
@@ -396,7 +454,7 @@ __device__ __noinline__ void helper_main(const TmParams& P, uint32_t tbase, int 
         uint32_t tcol = tbase;
         int sub = 0;
 #pragma unroll 1
-        for (int k32 = 0; k32 < kCols / 32; ++k32) {
+        for (int k32 = 0; k32 < kUnits; ++k32) {
           float4 v[8];
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) v[jj] = src[jj];
@@ -416,80 +474,82 @@ __device__ __noinline__ void helper_main(const TmParams& P, uint32_t tbase, int 
         mbar_arrive_u32(bars + 8u * (B_TM_FULL + q));
         mbar_arrive_u32(bars + 8u * (B_IN_FREE + fb));
       }
-      if (++fb == nbuf) {
+      if (++fb == kNBuf) {
         fb = 0;
         fpar ^= 1u;
       }
-      if (ti > 0) {  // the previous tile's rows of this quarter: one 384-byte store per lane
+      if (to_load > 0) VND_ISSUE_LOAD();
+      if (ti > 0 && lane == 0) {  // the previous tile's 32 rows of this quarter
         mbar_wait_u32(bars + 8u * (B_ST_FULL + q), tpar ^ 1u);
-        bulk_s2g_u32(ynext, stage_row, kR * 4u);
+        tma_store_3d(tmy, 0, store_row, r.c, stage_q);
         bulk_commit();
-        ynext += kTile;
-      }
-      if (loads_left > 0) VND_ISSUE_LOAD();
-      if (ti > 0) {
         bulk_wait_read0();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_u32(bars + 8u * (B_ST_FREE + q));
+        mbar_arrive_u32(bars + 8u * (B_ST_FREE + q));
       }
+      if (ti > 0) store_row += kRows;
+      __syncwarp();
       tpar ^= 1u;
     }
 #undef VND_ISSUE_LOAD
-    mbar_wait_u32(bars + 8u * (B_ST_FULL + q), tpar ^ 1u);
-    bulk_s2g_u32(ynext, stage_row, kR * 4u);
-    bulk_commit();
-    bulk_wait_read0();
+    if (lane == 0) {
+      mbar_wait_u32(bars + 8u * (B_ST_FULL + q), tpar ^ 1u);
+      tma_store_3d(tmy, 0, store_row, r.c, stage_q);
+      bulk_commit();
+      bulk_wait_read0();
+      mbar_arrive_u32(bars + 8u * (B_ST_FREE + q));
+    }
     __syncwarp();
-    if (lane == 0) mbar_arrive_u32(bars + 8u * (B_ST_FREE + q));
   }
 }
 
 // ---------------------------------------------------------------- compute warp (q, g)
 __device__ __noinline__ void compute_main(const TmParams& P, uint32_t tbase, int tid) {
   const Smem sm(P);
-  const int nbuf = P.nbuf, n_runs = P.n_runs, apply_gain = P.f.apply_gain;  // P lives behind a generic pointer here
+  const int n_runs = P.n_runs, apply_gain = P.f.apply_gain;  // P lives behind a generic pointer here
   const int lane = tid & 31, warp = tid >> 5;
   const int q = warp & 3, g = warp >> 2;
   const int m = 32 * q + lane;
   uint64_t* bars = sm.bars;
   const uint32_t tcol0 = tbase + (uint32_t)(kRG * g);  // column of this thread's first output
-  int it = 0;
+  int b = 0;           // ring slot of the current tile
+  unsigned fpar = 0;   // in_full parity of slot b
+  unsigned tpar = 0;   // parity of the tile counter (TMEM and staging barriers)
   for (int run = blockIdx.x; run < n_runs; run += gridDim.x) {
     RunInfo r;
     if (!begin_run(P, sm, run, tid, r)) continue;
     const int S = sm.sprog[0];
     const int near_end = *sm.s_near_end;
     for (int ti = 0; ti < r.n_tiles; ++ti) {
-      const int j = it + ti;
-      const int b = j % nbuf, u = j / nbuf;
       const float* row = sm.in_all + b * sm.bufw + m * kPitch;
       float yv[kRG];
 #pragma unroll
-      for (int r = 0; r < kRG; ++r) yv[r] = 0.0f;
-      const int* tp = sm.sprog + 1 + 3 * S;
-      mbar_wait(&bars[B_IN_FULL + b], u & 1);
-      mbar_wait(&bars[B_TM_FULL + q], j & 1);
+      for (int rr = 0; rr < kRG; ++rr) yv[rr] = 0.0f;
+      const int* ops = sm.ops + g * sm.opstride;
+      mbar_wait(&bars[B_IN_FULL + b], fpar);
+      mbar_wait(&bars[B_TM_FULL + q], tpar);
       tmem_fence_after();
-      run_segments<false>(sm.sprog, 0, near_end, tp, apply_gain, kRG * g, tcol0, row, yv);
+      run_segments<false>(sm.sprog, 0, near_end, ops, apply_gain, tcol0, row, yv);
       tmem_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_TM_FREE + q]);  // the helper may fill TMEM for the next tile
-      run_segments<true>(sm.sprog, near_end, S, tp, apply_gain, kRG * g, tcol0, row, yv);
+      run_segments<true>(sm.sprog, near_end, S, ops, apply_gain, tcol0, row, yv);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[B_IN_FREE + b]);
-      mbar_wait(&bars[B_ST_FREE + q], (j & 1) ^ 1);  // the previous tile's stores have read the staging rows
+      if (lane == 0) mbar_arrive(&bars[B_IN_FREE + b]);  // this warp is done with the tile buffer
+      mbar_wait(&bars[B_ST_FREE + q], tpar ^ 1u);  // the previous tile's stores have read the staging rows
       {
         float4* dst = reinterpret_cast<float4*>(sm.stage + m * kPitch + kRG * g);
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          dst[jj] = make_float4(yv[4 * jj], yv[4 * jj + 1], yv[4 * jj + 2], yv[4 * jj + 3]);
-        }
+        for (int jj = 0; jj < 8; ++jj) dst[jj] = make_float4(yv[4 * jj], yv[4 * jj + 1], yv[4 * jj + 2], yv[4 * jj + 3]);
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_ST_FULL + q]);
+      tpar ^= 1u;
+      if (++b == kNBuf) {
+        b = 0;
+        fpar ^= 1u;
+      }
     }
-    it += r.n_tiles;
   }
 }
 
@@ -500,15 +560,15 @@ __global__ void __launch_bounds__(kNT, 1) fir_tmem_kernel(const __grid_constant_
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   if (tid == 0) {
-    for (int b = 0; b < 3; ++b) {
+    for (int b = 0; b < kNBuf; ++b) {
       mbar_init(&sm.bars[B_IN_FULL + b], 1);
-      mbar_init(&sm.bars[B_IN_FREE + b], kNW);
+      mbar_init(&sm.bars[B_IN_FREE + b], kCW + 4);
     }
     for (int k = 0; k < 4; ++k) {
-      mbar_init(&sm.bars[B_TM_FULL + k], 1);
-      mbar_init(&sm.bars[B_TM_FREE + k], kG);
       mbar_init(&sm.bars[B_ST_FULL + k], kG);
       mbar_init(&sm.bars[B_ST_FREE + k], 1);
+      mbar_init(&sm.bars[B_TM_FULL + k], 1);
+      mbar_init(&sm.bars[B_TM_FREE + k], kG);
     }
     mbar_fence_init();
   }
@@ -531,6 +591,32 @@ __global__ void __launch_bounds__(kNT, 1) fir_tmem_kernel(const __grid_constant_
 
 }  // namespace
 
+// cuTensorMapEncodeTiled through the runtime (no link against libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) p = nullptr;
+    (void)cudaGetLastError();
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// base[c * stride_c + row * 96 + k] as a (96, rows, channels) float32 tensor with a (100, box_rows, 1) box
+static bool encode_rows(CUtensorMap* tm, const void* base, long long frames, long long stride_c, int channels, int box_rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)kR, (cuuint64_t)(frames / kR), (cuuint64_t)channels};
+  const cuuint64_t strides[2] = {(cuuint64_t)kR * 4u, (cuuint64_t)stride_c * 4u};
+  const cuuint32_t box[3] = {(cuuint32_t)kPitch, (cuuint32_t)box_rows, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // Runs the interior tiles of every channel and reports the frames covered per channel in
 // *frames_done (a multiple of the tile).  VND_EUNSUPPORTED (no error text) when the request does
 // not qualify; the caller then uses the other kernels for everything.
@@ -540,21 +626,24 @@ int fir_tmem_launch(const FirParams& f, int max_prog_words, cudaStream_t st, lon
   if ((reinterpret_cast<uintptr_t>(f.y) % 16) != 0 || (f.y_sc % 4) != 0) return VND_EUNSUPPORTED;
   int nblk = kRows + (f.halo + 4 + kR - 1) / kR;
   if (nblk < kRows + 6) nblk = kRows + 6;  // the TMEM fill reads 512 columns of every row
-  const size_t fixed = kBarBytes + (size_t)kRows * kPitch * 4 + (size_t)(max_prog_words + 4) * 4;
-  const size_t per_buf = (size_t)nblk * kPitch * 4;
-  int nbuf = 3;
-  if (fixed + 3 * per_buf > (size_t)kMaxDynSmem) nbuf = 2;
-  if (fixed + nbuf * per_buf > (size_t)kMaxDynSmem) return VND_EUNSUPPORTED;
-  if (f.frames < (long long)nblk * kR + 3LL * kTile) return VND_EUNSUPPORTED;  // fewer than four interior tiles
-  const size_t smem = fixed + nbuf * per_buf;
+  const int opstride = max_prog_words + 4;
+  const size_t bufw = ((size_t)nblk * kPitch + 31) & ~(size_t)31;
+  const size_t smem = kBarBytes + kNBuf * bufw * 4 + (size_t)kRows * kPitch * 4 + (size_t)(1 + kG) * opstride * 4;
+  if (smem > (size_t)kMaxDynSmem || nblk > 256) return VND_EUNSUPPORTED;  // a TMA box has at most 256 rows
+  if (f.channels > 1 && (f.x_sc % 4 != 0 || f.x_sc < f.frames || f.y_sc < f.frames)) return VND_EUNSUPPORTED;
+  const long long span = (long long)nblk * kR;  // samples a tile's bulk loads touch
+  if (f.frames < span + 3LL * kTile) return VND_EUNSUPPORTED;  // fewer than four interior tiles
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
   TmParams P{};
   P.f = f;
   P.nblk = nblk;
-  P.nbuf = nbuf;
-  const long long tiles = (f.frames - (long long)nblk * kR) / kTile + 1;
+  P.opstride = opstride;
+  const long long sx = f.channels > 1 ? f.x_sc : f.frames, sy = f.channels > 1 ? f.y_sc : f.frames;
+  if (!encode_rows(&P.tmx, f.x, f.frames, sx, f.channels, nblk) || !encode_rows(&P.tmy, f.y, f.frames, sy, f.channels, 32))
+    return VND_EUNSUPPORTED;  // no tensor-map encoder in this driver: the other kernels take over
+  const long long tiles = (f.frames - span) / kTile + 1;
   if (tiles > 0x3fffffffLL / (f.channels > 0 ? f.channels : 1)) return VND_EUNSUPPORTED;
   P.tiles_per_channel = (int)tiles;
   P.tiles_per_run = (int)(tiles < VND_TM_RUN ? tiles : VND_TM_RUN);
