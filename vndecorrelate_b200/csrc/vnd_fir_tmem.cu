@@ -43,8 +43,11 @@
 #include "vnd_common.cuh"
 #include "vnd_fir.cuh"
 
-#ifndef VND_TM_RUN
-#define VND_TM_RUN 64  // consecutive tiles of one channel per CTA run
+#ifndef VND_TM_RUN_MAX
+#define VND_TM_RUN_MAX 512  // most consecutive tiles of one channel in a CTA run
+#endif
+#ifndef VND_TM_RUN_MIN
+#define VND_TM_RUN_MIN 48   // fewest (a run pays a prologue and a pipeline fill of about two tiles)
 #endif
 
 namespace vnd {
@@ -646,8 +649,26 @@ int fir_tmem_launch(const FirParams& f, int max_prog_words, cudaStream_t st, lon
   const long long tiles = (f.frames - span) / kTile + 1;
   if (tiles > 0x3fffffffLL / (f.channels > 0 ? f.channels : 1)) return VND_EUNSUPPORTED;
   P.tiles_per_channel = (int)tiles;
-  P.tiles_per_run = (int)(tiles < VND_TM_RUN ? tiles : VND_TM_RUN);
-  P.runs_per_channel = (int)ceil_div<long long>(tiles, P.tiles_per_run);
+  {  // split every channel into equal runs so that the persistent CTAs finish together: pick the number of
+     // runs per channel that minimises (waves of runs) x (tiles per run + two tiles of prologue)
+    long long best_cost = -1;
+    int best_rpc = 1;
+    const long long rpc_lo = ceil_div<long long>(tiles, VND_TM_RUN_MAX);
+    long long rpc_hi = tiles / VND_TM_RUN_MIN;
+    if (rpc_hi < rpc_lo) rpc_hi = rpc_lo;
+    for (long long rpc = rpc_lo; rpc <= rpc_hi; ++rpc) {
+      const long long tpr = ceil_div<long long>(tiles, rpc);
+      const long long real_rpc = ceil_div<long long>(tiles, tpr);
+      const long long waves = ceil_div<long long>(real_rpc * f.channels, di.sm_count);
+      const long long cost = waves * (tpr + 2);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best_rpc = (int)real_rpc;
+      }
+    }
+    P.tiles_per_run = (int)ceil_div<long long>(tiles, best_rpc);
+    P.runs_per_channel = (int)ceil_div<long long>(tiles, P.tiles_per_run);
+  }
   P.n_runs = P.runs_per_channel * f.channels;
   VND_CUDA_OK(cudaFuncSetAttribute(fir_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = di.sm_count;
