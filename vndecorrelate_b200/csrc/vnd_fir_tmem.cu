@@ -180,6 +180,7 @@ struct TmParams {
   FirParams f;
   int nblk;      // 96-sample blocks staged per tile (tile + halo)
   int opstride;  // words reserved for the program and for each decoded list
+  int stagger_ns;  // start-of-run delay between lane quarters (see stagger())
   int tiles_per_run;
   int runs_per_channel;
   int n_runs;
@@ -408,12 +409,23 @@ __device__ __forceinline__ bool begin_run(const TmParams& P, const Smem& sm, int
   return true;
 }
 
+// The four lane quarters run the same tile pipeline on four schedulers but share ONE shared-memory
+// pipe, which the far taps and the TMEM refill load heavily while the tensor-memory taps do not use
+// it at all.  Started together, the quarters stay in phase: the pipe saturates while everybody is in
+// the far-tap phase and idles during the tensor-memory phase (ncu: issue slots and the shared-memory
+// pipe each ~50 % busy).  Delaying quarter q by q x 3 us (half a tile) at the start of every run interleaves
+// the phases; nothing couples the quarters tightly enough to pull them back (the tile ring is three
+// deep, TMEM and staging hand-overs are per quarter).
+__device__ __forceinline__ void stagger(int q, int ns) {
+  for (int k = 0; k < q; ++k) __nanosleep((unsigned)ns);
+}
+
 // ---------------------------------------------------------------- data-movement warp of lane quarter q
 // One elected lane per warp: quarter 0 issues the tile loads (one TMA request per tile, three tiles
 // ahead), every quarter stores its own 32 staged rows (one request per tile).
 __device__ __noinline__ void helper_main(const TmParams& P, uint32_t tbase, int tid) {
   const Smem sm(P);
-  const int nblk = P.nblk, n_runs = P.n_runs;  // P lives behind a generic pointer here
+  const int nblk = P.nblk, n_runs = P.n_runs, stagger_ns = P.stagger_ns;  // P lives behind a generic pointer here
   const int lane = tid & 31, q = (tid >> 5) & 3;
   const int m = 32 * q + lane;
   const uint32_t bars = smem_u32(sm.bars), in0 = smem_u32(sm.in_all), buf_bytes = (uint32_t)sm.bufw * 4u;
@@ -428,6 +440,7 @@ __device__ __noinline__ void helper_main(const TmParams& P, uint32_t tbase, int 
   for (int run = blockIdx.x; run < n_runs; run += gridDim.x) {
     RunInfo r;
     if (!begin_run(P, sm, run, tid, r)) continue;
+    stagger(q, stagger_ns);
     int load_row = r.first_tile * kRows;  // first row (96 samples) of the next tile to load
     int store_row = r.first_tile * kRows + 32 * q;
     int to_load = r.n_tiles;
@@ -508,7 +521,7 @@ __device__ __noinline__ void helper_main(const TmParams& P, uint32_t tbase, int 
 // ---------------------------------------------------------------- compute warp (q, g)
 __device__ __noinline__ void compute_main(const TmParams& P, uint32_t tbase, int tid) {
   const Smem sm(P);
-  const int n_runs = P.n_runs, apply_gain = P.f.apply_gain;  // P lives behind a generic pointer here
+  const int n_runs = P.n_runs, apply_gain = P.f.apply_gain, stagger_ns = P.stagger_ns;  // P lives behind a generic pointer here
   const int lane = tid & 31, warp = tid >> 5;
   const int q = warp & 3, g = warp >> 2;
   const int m = 32 * q + lane;
@@ -520,6 +533,7 @@ __device__ __noinline__ void compute_main(const TmParams& P, uint32_t tbase, int
   for (int run = blockIdx.x; run < n_runs; run += gridDim.x) {
     RunInfo r;
     if (!begin_run(P, sm, run, tid, r)) continue;
+    stagger(q, stagger_ns);
     const int S = sm.sprog[0];
     const int near_end = *sm.s_near_end;
     for (int ti = 0; ti < r.n_tiles; ++ti) {
@@ -594,6 +608,12 @@ __global__ void __launch_bounds__(kNT, 1) fir_tmem_kernel(const __grid_constant_
 
 }  // namespace
 
+// VND_TM_STAGGER_NS overrides the start-of-run delay between lane quarters (tuning).
+static const int g_stagger_ns = [] {
+  const char* e = getenv("VND_TM_STAGGER_NS");
+  return e ? atoi(e) : 3000;
+}();
+
 // cuTensorMapEncodeTiled through the runtime (no link against libcuda).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -643,6 +663,7 @@ int fir_tmem_launch(const FirParams& f, int max_prog_words, cudaStream_t st, lon
   P.f = f;
   P.nblk = nblk;
   P.opstride = opstride;
+  P.stagger_ns = g_stagger_ns;
   const long long sx = f.channels > 1 ? f.x_sc : f.frames, sy = f.channels > 1 ? f.y_sc : f.frames;
   if (!encode_rows(&P.tmx, f.x, f.frames, sx, f.channels, nblk) || !encode_rows(&P.tmy, f.y, f.frames, sy, f.channels, 32))
     return VND_EUNSUPPORTED;  // no tensor-map encoder in this driver: the other kernels take over
