@@ -290,7 +290,7 @@ def run_b200(args) -> None:
     achieved = BYTES_PER_SAMPLE * Cg * L / (kernel_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak_gbs()
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "fir_tile_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "fir_tile_traffic.json" if os.environ.get("VND_DISABLE_TMEM") == "1" else "fir_tmem_traffic.json")
     if os.path.exists(tpath):
         try:
             tr = json.load(open(tpath))
