@@ -481,3 +481,33 @@ def test_optimisers_short_excerpt(api):
     a = api.VelvetNoise(sample_rate_hz=fs, num_impulses=ref["num_impulses"], log_distribution_strength=k, filtered_channels=(0,), mode="LR", seed=1)
     b = api.VelvetNoise(sample_rate_hz=fs, num_impulses=ref["num_impulses"], log_distribution_strength=ref["kappa"], filtered_channels=(0,), mode="LR", seed=1)
     assert abs(k - ref["kappa"]) <= 1e-3 or a.velvet_noise == b.velvet_noise
+
+
+def test_batched_refinement_equals_one_at_a_time(api):
+    """Lock-step Brent (one launch per iteration over all local minima) returns exactly what the
+    reference's loop over minima returns with the same objective (optimization.py:131-155)."""
+    from vndecorrelate_b200 import optimization as OPT
+
+    fs, viola = G.wav("viola")
+    sig = viola[60000:90000]
+    kw = dict(angle_limit=np.pi / 4, lambda_mean=5.0, lambda_skew=2.0, lambda_correlation=15.0, lambda_penalty=1e3)
+
+    def candidate(kappa):
+        return api.VelvetNoise(sample_rate_hz=fs, duration_seconds=0.03, num_impulses=15, log_distribution_strength=kappa, normalizer=None,
+                               filtered_channels=(0,), mode="LR", seed=1)
+
+    grid = 48
+    kappas = np.linspace(0.0, 1.0, grid)
+    scores = OPT.grid_scan(sig, [candidate(k) for k in kappas], **kw)
+    minima = OPT.get_local_minima(scores, grid)
+    one_at_a_time = OPT.optimize_local_minima(minima, kappas, grid, lambda k: OPT.symmetry_aware_objective(sig, candidate(k), **kw))
+    batched = OPT.optimize_velvet_noise(input_signal=sig, sample_rate_hz=fs, duration_seconds=0.03, num_impulses=15, seed=1, grid_size=grid)
+    assert batched == one_at_a_time
+
+    taus = np.linspace(0.0, 0.03, grid)
+    scores = OPT.grid_scan(sig, [api.HaasEffect(sample_rate_hz=fs, delay_time_seconds=t, mode="LR") for t in taus], **kw)
+    minima = OPT.get_local_minima(scores, grid)
+    one_at_a_time = OPT.optimize_local_minima(
+        minima, taus, grid, lambda t: OPT.symmetry_aware_objective(sig, api.HaasEffect(sample_rate_hz=fs, delay_time_seconds=t, mode="LR"), **kw))
+    batched = OPT.optimize_haas_delay(input_signal=sig, sample_rate_hz=fs, max_delay_seconds=0.03, grid_size=grid)
+    assert batched == one_at_a_time

@@ -302,3 +302,52 @@ def test_no_gpu_means_loud_failure_not_fallback():
     assert b"no CPU fallback" in N.lib().vnd_last_error()
     with pytest.raises(N.VndError):
         VelvetNoise(sample_rate_hz=44100, seed=1).decorrelate(np.zeros((100, 2), np.float32))
+
+
+# ------------------------------------------------------------------ lock-step Brent refinement
+
+
+def test_lockstep_minimize_equals_scipy_one_at_a_time():
+    """The lock-step engine runs scipy's own bounded minimiser per interval, so abscissae, values and
+    evaluation counts must equal the sequential loop of the reference (optimization.py:131-155),
+    including on a piecewise-constant objective like the velvet-noise one."""
+    from scipy.optimize import minimize_scalar
+
+    from vndecorrelate_b200.optimization import lockstep_minimize, optimize_local_minima, optimize_local_minima_batched
+
+    def f(x):
+        return np.float32(np.floor(40.0 * np.sin(7.0 * x) ** 2) / 40.0 + 0.3 * (x - 0.55) ** 2)
+
+    bounds = [(0.0, 0.1), (0.1, 0.35), (0.3, 0.5), (0.45, 0.7), (0.7, 1.0), (0.2, 0.2000001)]
+    calls = []
+
+    def batch(xs):
+        calls.append(len(xs))
+        return [f(x) for x in xs]
+
+    got = lockstep_minimize(bounds, batch, xatol=1e-4)
+    for (lo, hi), g in zip(bounds, got):
+        want = minimize_scalar(fun=f, bounds=(lo, hi), method="bounded", options={"xatol": 1e-4})
+        assert g.x == want.x and g.fun == want.fun and g.nfev == want.nfev
+    assert calls[0] == len(bounds) and sum(calls) == sum(g.nfev for g in got)  # every batch holds all live minimisers
+    assert len(calls) == max(g.nfev for g in got)
+
+    # selection rule of the reference: bounds from the grid neighbours, first strictly best wins
+    grid = np.linspace(0.0, 1.0, 21)
+    scores = np.array([f(x) for x in grid])
+    minima = [i for i in range(1, 20) if scores[i] < scores[i - 1] and scores[i] < scores[i + 1]]
+    assert minima
+    a = optimize_local_minima(minima, grid, 21, f)
+    b = optimize_local_minima_batched(minima, grid, 21, lambda xs: [f(x) for x in xs])
+    assert a == b
+    assert lockstep_minimize([], batch) == []
+
+
+def test_lockstep_minimize_propagates_errors():
+    from vndecorrelate_b200.optimization import lockstep_minimize
+
+    def bad(xs):
+        raise ValueError("boom")
+
+    with pytest.raises(ValueError, match="boom"):
+        lockstep_minimize([(0.0, 1.0), (1.0, 2.0)], bad)

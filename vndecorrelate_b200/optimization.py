@@ -289,6 +289,108 @@ def optimize_local_minima(local_minima: list[int], scalars, grid_size: int, scal
     return best_scalar
 
 
+def lockstep_minimize(bounds: Sequence[tuple[float, float]], batch_objective: Callable[[list[float]], Sequence[Any]], *, xatol: float = 1e-4):
+    """Run scipy's bounded Brent minimiser on many intervals at once, in lock-step.
+
+    Every interval gets its own ``scipy.optimize.minimize_scalar(method="bounded")`` — the reference's
+    refinement step (optimization.py:144-149), unchanged, so every comparison it makes is the one the
+    reference makes — running in its own thread.  Whenever all live minimisers are waiting for a
+    function value, the pending abscissae are evaluated with ONE call of ``batch_objective`` (one
+    kernel launch over all of them) and handed back.  Returns the ``OptimizeResult`` list in input
+    order.  The sequence of abscissae each minimiser sees depends only on its own function values, so
+    the results equal those of the one-at-a-time loop whenever ``batch_objective`` returns the values
+    the scalar objective would."""
+    import threading
+
+    from scipy.optimize import minimize_scalar
+
+    n = len(bounds)
+    if n == 0:
+        return []
+    cond = threading.Condition()
+    pending: dict[int, float] = {}
+    answers: dict[int, Any] = {}
+    results: list[Any] = [None] * n
+    errors: list[BaseException] = []
+    alive = n
+
+    def worker(i: int, lo: float, hi: float) -> None:
+        nonlocal alive
+
+        def fn(x):
+            with cond:
+                pending[i] = float(x)
+                cond.notify_all()
+                while i not in answers and not errors:
+                    cond.wait()
+                if errors:
+                    raise RuntimeError("lock-step evaluation failed") from errors[0]
+                return answers.pop(i)
+
+        try:
+            results[i] = minimize_scalar(fun=fn, bounds=(lo, hi), method="bounded", options={"xatol": xatol})
+        except BaseException as exc:  # surfaced by the coordinator
+            with cond:
+                errors.append(exc)
+        finally:
+            with cond:
+                alive -= 1
+                cond.notify_all()
+
+    threads = [threading.Thread(target=worker, args=(i, lo, hi), daemon=True) for i, (lo, hi) in enumerate(bounds)]
+    for t in threads:
+        t.start()
+    with cond:
+        while alive > 0 and not errors:
+            while len(pending) < alive and alive > 0 and not errors:
+                cond.wait()
+            if errors or alive == 0:
+                break
+            ids = sorted(pending)
+            xs = [pending.pop(i) for i in ids]
+            try:
+                vals = batch_objective(xs)
+            except BaseException as exc:
+                errors.append(exc)
+                cond.notify_all()
+                break
+            for i, v in zip(ids, vals):
+                answers[i] = v
+            cond.notify_all()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return results
+
+
+def optimize_local_minima_batched(local_minima: list[int], scalars, grid_size: int, batch_objective: Callable[[list[float]], Sequence[Any]]):
+    """``optimize_local_minima`` with all minima refined in lock-step (one launch per Brent iteration
+    instead of one per evaluation); same bounds, same ``xatol``, same first-strictly-best rule
+    (optimization.py:131-155)."""
+    print("Starting Local Minima optimization")
+    bounds = [(scalars[max(0, i - 1)], scalars[min(grid_size - 1, i + 1)]) for i in local_minima]
+    best_scalar, best_score = 0.0, np.inf
+    for result in lockstep_minimize(bounds, batch_objective, xatol=1e-4):
+        if result.fun < best_score:
+            best_score = result.fun
+            best_scalar = result.x
+    return best_scalar
+
+
+def _device_clip(x: np.ndarray):
+    """The clip as a resident planar CUDA tensor (uploaded once per optimisation) when torch is there;
+    otherwise the numpy array itself (the host entry points then upload it on every call)."""
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            return torch.from_numpy(np.ascontiguousarray(x.T)[None]).to(f"cuda:{R.default_device()}")
+    except ImportError:
+        pass
+    return x
+
+
 def optimize_haas_delay(*, input_signal, sample_rate_hz: int, max_delay_seconds: int, grid_size: int = 400, angle_limit: float = np.pi / 4,
                         lambda_mean: float = 5.0, lambda_skew: float = 2.0, lambda_correlation: float = 15.0, lambda_penalty: float = 1e3) -> float:
     """Optimised ``delay_time_seconds`` in ``[0, max_delay_seconds]`` (optimization.py:158-227)."""
@@ -298,10 +400,15 @@ def optimize_haas_delay(*, input_signal, sample_rate_hz: int, max_delay_seconds:
     candidates = [HaasEffect(sample_rate_hz=sample_rate_hz, delay_time_seconds=tau, mode="LR") for tau in taus]
     scores = grid_scan(input_signal, candidates, **kw)
     local_minima = get_local_minima(scores, grid_size)
-    return optimize_local_minima(
-        local_minima, taus, grid_size,
-        lambda tau: symmetry_aware_objective(input_signal, HaasEffect(sample_rate_hz=sample_rate_hz, delay_time_seconds=tau, mode="LR"), **kw),
-    )
+    clip = _device_clip(_as_stereo_f32(input_signal))
+
+    def batch(ts):
+        delays = [HaasEffect(sample_rate_hz=sample_rate_hz, delay_time_seconds=t, mode="LR").delay_len_samples for t in ts]
+        p = haas_objective_partials(clip, delays)
+        p = p.cpu().numpy() if R.is_torch_tensor(p) else p
+        return list(haas_scores_from_partials(p, **kw)[0])
+
+    return optimize_local_minima_batched(local_minima, taus, grid_size, batch)
 
 
 def optimize_velvet_noise(*, input_signal, sample_rate_hz: int, duration_seconds: float, num_impulses: int, seed: int = 1, grid_size: int = 400,
@@ -318,4 +425,13 @@ def optimize_velvet_noise(*, input_signal, sample_rate_hz: int, duration_seconds
     kappas = np.linspace(0.0, 1.0, grid_size)
     scores = grid_scan(input_signal, [candidate(k) for k in kappas], **kw)
     local_minima = get_local_minima(scores, grid_size)
-    return optimize_local_minima(local_minima, kappas, grid_size, lambda kappa: symmetry_aware_objective(input_signal, candidate(kappa), **kw))
+    x = _as_stereo_f32(input_signal)
+    clip = _device_clip(x)
+
+    def batch(ks):
+        prog = _vn_family_program([candidate(k) for k in ks], x.shape[0])
+        p = vn_objective_partials(clip, prog)
+        p = p.cpu().numpy() if R.is_torch_tensor(p) else p
+        return list(vn_scores_from_partials(p, **kw)[0])
+
+    return optimize_local_minima_batched(local_minima, kappas, grid_size, batch)
