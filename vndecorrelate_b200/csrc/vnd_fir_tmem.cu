@@ -50,6 +50,22 @@
 #define VND_TM_RUN_MIN 48   // fewest (a run pays a prologue and a pipeline fill of about two tiles)
 #endif
 
+#ifdef VND_TM_TRACE
+// Debug builds only: clock64() of a few events per warp and tile of CTA 0 (tools/trace_tmem.py).
+__device__ unsigned long long g_tm_trace[16][64][8];
+#define VND_TRACE(tile, ev)                                                                    \
+  do {                                                                                         \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (tile) < 64) g_tm_trace[threadIdx.x >> 5][tile][ev] = clock64(); \
+  } while (0)
+extern "C" int vnd_debug_tm_trace(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_tm_trace, sizeof(g_tm_trace));
+}
+#else
+#define VND_TRACE(tile, ev) \
+  do {                      \
+  } while (0)
+#endif
+
 namespace vnd {
 
 namespace {
@@ -463,8 +479,10 @@ __device__ __noinline__ void helper_main(const TmParams& P, uint32_t tbase, int 
     for (int d = 0; d < kNBuf - 1 && to_load > 0; ++d) VND_ISSUE_LOAD();
     for (int ti = 0; ti < r.n_tiles; ++ti) {
       mbar_wait_u32(bars + 8u * (B_IN_FULL + fb), fpar);
+      VND_TRACE(ti, 4);
       mbar_wait_u32(bars + 8u * (B_TM_FREE + q), tpar ^ 1u);  // the quarter is past its last TMEM tap of the previous tile
       tmem_fence_after();
+      VND_TRACE(ti, 0);
       {  // fill row m: 32 columns per step; a block of 96 samples is three steps, then the pitch skips 4 words
         const float4* src = reinterpret_cast<const float4*>(sm.in_all + fb * sm.bufw + m * kPitch);
         uint32_t tcol = tbase;
@@ -486,6 +504,7 @@ __device__ __noinline__ void helper_main(const TmParams& P, uint32_t tbase, int 
       }
       tmem_fence_before();
       __syncwarp();
+      VND_TRACE(ti, 1);
       if (lane == 0) {
         mbar_arrive_u32(bars + 8u * (B_TM_FULL + q));
         mbar_arrive_u32(bars + 8u * (B_IN_FREE + fb));
@@ -504,6 +523,7 @@ __device__ __noinline__ void helper_main(const TmParams& P, uint32_t tbase, int 
       }
       if (ti > 0) store_row += kRows;
       __syncwarp();
+      VND_TRACE(ti, 2);
       tpar ^= 1u;
     }
 #undef VND_ISSUE_LOAD
@@ -542,17 +562,22 @@ __device__ __noinline__ void compute_main(const TmParams& P, uint32_t tbase, int
 #pragma unroll
       for (int rr = 0; rr < kRG; ++rr) yv[rr] = 0.0f;
       const int* ops = sm.ops + g * sm.opstride;
+      VND_TRACE(ti, 0);
       mbar_wait(&bars[B_IN_FULL + b], fpar);
       mbar_wait(&bars[B_TM_FULL + q], tpar);
       tmem_fence_after();
+      VND_TRACE(ti, 1);
       run_segments<false>(sm.sprog, 0, near_end, ops, apply_gain, tcol0, row, yv);
+      VND_TRACE(ti, 2);
       tmem_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_TM_FREE + q]);  // the helper may fill TMEM for the next tile
       run_segments<true>(sm.sprog, near_end, S, ops, apply_gain, tcol0, row, yv);
+      VND_TRACE(ti, 3);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_IN_FREE + b]);  // this warp is done with the tile buffer
-      mbar_wait(&bars[B_ST_FREE + q], tpar ^ 1u);  // the previous tile's stores have read the staging rows
+      mbar_wait(&bars[B_ST_FREE + q], tpar ^ 1u);
+      VND_TRACE(ti, 5);  // the previous tile's stores have read the staging rows
       {
         float4* dst = reinterpret_cast<float4*>(sm.stage + m * kPitch + kRG * g);
 #pragma unroll
@@ -560,6 +585,7 @@ __device__ __noinline__ void compute_main(const TmParams& P, uint32_t tbase, int
       }
       fence_proxy_async();
       __syncwarp();
+      VND_TRACE(ti, 4);
       if (lane == 0) mbar_arrive(&bars[B_ST_FULL + q]);
       tpar ^= 1u;
       if (++b == kNBuf) {
