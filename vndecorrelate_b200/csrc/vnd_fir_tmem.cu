@@ -288,16 +288,43 @@ __device__ __forceinline__ void one_tap(int op, uint32_t tcol0, const float* __r
 
 // One list of taps applied to acc: the negative impulses of a segment (SUB) or the positive ones.
 // ALLFAR: no tap of the list lies inside the TMEM window (no tensor-memory code at all).
-// The loop is unrolled by two with the operation words in alternating registers, so that each word
+// `nn` = number of LEADING taps of the list that are tensor-memory taps (impulses come in ascending
+// order, so that is normally all of them): they run in a loop without the per-tap near/far decision.
+// The loops are unrolled by two with the operation words in alternating registers, so that each word
 // is loaded a whole tap before it is needed and never copied (a single loop-carried register made
 // ptxas copy the loaded word at once and stall on the shared-memory latency at every tap).
 template <bool SUB, bool ALLFAR>
-__device__ __forceinline__ void tap_list(const int* __restrict__ ops, int n, uint32_t tcol0, const float* __restrict__ row,
+__device__ __forceinline__ void tap_list(const int* __restrict__ ops, int n, int nn, uint32_t tcol0, const float* __restrict__ row,
                                          float (&acc)[kRG]) {
   if (n <= 0) return;
+  int k = 0;
   int op_a = ops[0];
-  for (int k = 0;; k += 2) {
-    const int op_b = ops[k + 1];  // two words of slack follow the lists, so the prefetches stay in bounds
+  if constexpr (!ALLFAR) {
+    for (; k < nn; k += 2) {  // near prefix
+      const int op_b = ops[k + 1];  // two words of slack follow the lists, so the prefetches stay in bounds
+      {
+        float t[kRG];
+        near_issue(t, tcol0 + (uint32_t)op_a);
+        tmem_wait_ld(t);
+        near_add<SUB>(t, acc);
+      }
+      op_a = ops[k + 2];
+      if (k + 1 >= nn) {
+        op_a = op_b;
+        ++k;
+        break;
+      }
+      {
+        float t[kRG];
+        near_issue(t, tcol0 + (uint32_t)op_b);
+        tmem_wait_ld(t);
+        near_add<SUB>(t, acc);
+      }
+    }
+    if (k >= n) return;
+  }
+  for (;; k += 2) {  // the rest: far taps (and any near tap behind a far one)
+    const int op_b = ops[k + 1];
     one_tap<SUB, ALLFAR>(op_a, tcol0, row, acc);
     if (k + 1 >= n) break;
     op_a = ops[k + 2];
@@ -310,16 +337,17 @@ __device__ __forceinline__ void tap_list(const int* __restrict__ ops, int n, uin
 // (decorrelation.py:402-414): acc = 0; acc -= x[n + i] over the negative list; acc += x[n + i] over
 // the positive list; acc *= gain; y += acc.
 template <bool ALLFAR>
-__device__ __forceinline__ void run_segments(const int* __restrict__ sprog, int s0, int s1, const int*& ops, int apply_gain,
-                                             uint32_t tcol0, const float* __restrict__ row, float (&yv)[kRG]) {
+__device__ __forceinline__ void run_segments(const int* __restrict__ sprog, const int* __restrict__ segnear, int s0, int s1, const int*& ops,
+                                             int apply_gain, uint32_t tcol0, const float* __restrict__ row, float (&yv)[kRG]) {
   const int* seg = sprog + 1;
   for (int s = s0; s < s1; ++s) {
     const int n_neg = seg[3 * s], n_pos = seg[3 * s + 1];
     float acc[kRG];
 #pragma unroll
     for (int r = 0; r < kRG; ++r) acc[r] = 0.0f;
-    tap_list<true, ALLFAR>(ops, n_neg, tcol0, row, acc);
-    tap_list<false, ALLFAR>(ops + n_neg, n_pos, tcol0, row, acc);
+    const int nn = ALLFAR ? 0 : segnear[s];  // leading tensor-memory taps: neg list in the low half, pos list in the high half
+    tap_list<true, ALLFAR>(ops, n_neg, nn & 0xffff, tcol0, row, acc);
+    tap_list<false, ALLFAR>(ops + n_neg, n_pos, nn >> 16, tcol0, row, acc);
     ops += n_neg + n_pos;
     if (apply_gain) {
       const float gain = __int_as_float(seg[3 * s + 2]);
@@ -349,6 +377,7 @@ struct Smem {
   float* stage;
   int* sprog;
   int* ops;  // [3][opstride]: decoded tap operations per thread group
+  int* segnear;  // per segment: leading tensor-memory taps of the negative (low 16 bits) and positive list
   int bufw;
   int opstride;
   __device__ __forceinline__ explicit Smem(const TmParams& P) {
@@ -360,6 +389,7 @@ struct Smem {
     sprog = reinterpret_cast<int*>(stage + kRows * kPitch);
     opstride = P.opstride;
     ops = sprog + opstride;
+    segnear = ops + kG * opstride;
   }
 };
 
@@ -396,9 +426,13 @@ __device__ __forceinline__ bool begin_run(const TmParams& P, const Smem& sm, int
     const int* tq = taps;
     int ne = 0;
     for (int s = 0; s < S; ++s) {
-      const int n = sm.sprog[1 + 3 * s] + sm.sprog[2 + 3 * s];
+      const int n_neg = sm.sprog[1 + 3 * s], n = n_neg + sm.sprog[2 + 3 * s];
       for (int k = 0; k < n; ++k)
         if (tq[k] <= kNearMax) ne = s + 1;
+      int a = 0, b = 0;  // leading tensor-memory taps of the two lists
+      while (a < n_neg && tq[a] <= kNearMax) ++a;
+      while (n_neg + b < n && tq[n_neg + b] <= kNearMax) ++b;
+      sm.segnear[s] = a | (b << 16);
       tq += n;
     }
     *sm.s_near_end = ne;
@@ -567,12 +601,12 @@ __device__ __noinline__ void compute_main(const TmParams& P, uint32_t tbase, int
       mbar_wait(&bars[B_TM_FULL + q], tpar);
       tmem_fence_after();
       VND_TRACE(ti, 1);
-      run_segments<false>(sm.sprog, 0, near_end, ops, apply_gain, tcol0, row, yv);
+      run_segments<false>(sm.sprog, sm.segnear, 0, near_end, ops, apply_gain, tcol0, row, yv);
       VND_TRACE(ti, 2);
       tmem_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_TM_FREE + q]);  // the helper may fill TMEM for the next tile
-      run_segments<true>(sm.sprog, near_end, S, ops, apply_gain, tcol0, row, yv);
+      run_segments<true>(sm.sprog, sm.segnear, near_end, S, ops, apply_gain, tcol0, row, yv);
       VND_TRACE(ti, 3);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_IN_FREE + b]);  // this warp is done with the tile buffer
@@ -677,7 +711,7 @@ int fir_tmem_launch(const FirParams& f, int max_prog_words, cudaStream_t st, lon
   if (nblk < kRows + 6) nblk = kRows + 6;  // the TMEM fill reads 512 columns of every row
   const int opstride = max_prog_words + 4;
   const size_t bufw = ((size_t)nblk * kPitch + 31) & ~(size_t)31;
-  const size_t smem = kBarBytes + kNBuf * bufw * 4 + (size_t)kRows * kPitch * 4 + (size_t)(1 + kG) * opstride * 4;
+  const size_t smem = kBarBytes + kNBuf * bufw * 4 + (size_t)kRows * kPitch * 4 + (size_t)(2 + kG) * opstride * 4;
   if (smem > (size_t)kMaxDynSmem || nblk > 256) return VND_EUNSUPPORTED;  // a TMA box has at most 256 rows
   if (f.channels > 1 && (f.x_sc % 4 != 0 || f.x_sc < f.frames || f.y_sc < f.frames)) return VND_EUNSUPPORTED;
   const long long span = (long long)nblk * kR;  // samples a tile's bulk loads touch
