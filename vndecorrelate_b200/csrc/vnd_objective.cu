@@ -27,7 +27,10 @@ namespace vnd {
 
 constexpr int OBJ_SLOTS = 12;  // doubles per (clip, candidate) partial, see vnd_b200.h
 constexpr int OBJ_NT = 512;
-constexpr int OBJ_R = 8;
+#ifndef VND_OBJ_R
+#define VND_OBJ_R 16
+#endif
+constexpr int OBJ_R = VND_OBJ_R;  // frames per lane and pass (even: the taps are applied with packed adds)
 constexpr int OBJ_TILE = 4096;
 
 struct ObjParams {
@@ -59,6 +62,30 @@ __device__ __forceinline__ float atan01(float t) {
   return p * t;
 }
 
+// Packed fp32 arithmetic (sm_100+): two IEEE round-to-nearest operations per instruction on an aligned
+// register pair (FADD2 / FMUL2 / FFMA2 in SASS): same bits as two scalar operations, half the issue slots.
+typedef unsigned long long obj_pair_t;
+#define VND_OBJ_PACKED(name, op)                                                   \
+  __device__ __forceinline__ void name(float& a0, float& a1, float b0, float b1) { \
+    obj_pair_t ra, rb;                                                             \
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));                   \
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));                   \
+    asm(op ".rn.f32x2 %0, %0, %1;" : "+l"(ra) : "l"(rb));                         \
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(ra));                  \
+  }
+VND_OBJ_PACKED(obj_add2, "add")
+VND_OBJ_PACKED(obj_sub2, "sub")
+VND_OBJ_PACKED(obj_mul2, "mul")
+// (a0, a1) = (a0, a1) * (b0, b1) + (c0, c1), one rounding each (FFMA2)
+__device__ __forceinline__ void obj_fma2(float& a0, float& a1, float b0, float b1, float c0, float c1) {
+  obj_pair_t ra, rb, rc;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c0), "f"(c1));
+  asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(ra) : "l"(rb), "l"(rc));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(ra));
+}
+
 struct LaneAcc {
   float sr, srt, srt2, srt3, slr, sll;
   float d_pos, s_pos, d_neg, s_neg;  // |d|, |s| of the frame with the largest |d|/|s| per sign of s
@@ -85,6 +112,78 @@ __device__ __forceinline__ void lane_acc_frame(LaneAcc& a, float l, float r_) {
     if (ad * a.s_pos > a.d_pos * as) { a.d_pos = ad; a.s_pos = as; }
   } else {
     if (ad * a.s_neg > a.d_neg * as) { a.d_neg = ad; a.s_neg = as; }
+  }
+}
+
+// Two frames at once with packed arithmetic.  The amplitude-weighted sums run in two interleaved
+// chains per lane (even / odd frames, slot [0] / [1]), added together before the warp reduction; the
+// ratio trackers stay scalar and see the frames in order.
+struct LaneAcc2 {
+  float sr[2], srt[2], srt2[2], srt3[2], slr[2], sll[2];
+  float d_pos, s_pos, d_neg, s_neg;
+};
+
+__device__ __forceinline__ float obj_theta(float t, float p, float ad, float as, float d, float s) {
+  float th = p * t;
+  if (ad > as) th = 1.57079632679489662f - th;
+  return __int_as_float(__float_as_int(th) | ((__float_as_int(d) ^ __float_as_int(s)) & 0x80000000));
+}
+
+__device__ __forceinline__ void lane_acc_pair(LaneAcc2& a, float l0, float l1, float r0, float r1) {
+  float d0 = l0, d1 = l1, s0 = l0, s1 = l1;
+  obj_sub2(d0, d1, r0, r1);  // utils/dsp.py:399-401
+  obj_add2(s0, s1, r0, r1);
+  const float ad0 = fabsf(d0), as0 = fabsf(s0), ad1 = fabsf(d1), as1 = fabsf(s1);
+  const float mx0 = fmaxf(ad0, as0), mn0 = fminf(ad0, as0), mx1 = fmaxf(ad1, as1), mn1 = fminf(ad1, as1);
+  const float t0 = mx0 > 0.0f ? __fdividef(mn0, mx0) : 0.0f, t1 = mx1 > 0.0f ? __fdividef(mn1, mx1) : 0.0f;
+  float z0 = t0, z1 = t1;
+  obj_mul2(z0, z1, t0, t1);
+  float p0 = 0.00245671847107214f, p1 = p0;  // atan01's polynomial on both frames
+  obj_fma2(p0, p1, z0, z1, -0.01440133168500584f, -0.01440133168500584f);
+  obj_fma2(p0, p1, z0, z1, 0.03978117728736144f, 0.03978117728736144f);
+  obj_fma2(p0, p1, z0, z1, -0.07234853052703884f, -0.07234853052703884f);
+  obj_fma2(p0, p1, z0, z1, 0.10498943808759016f, 0.10498943808759016f);
+  obj_fma2(p0, p1, z0, z1, -0.14161228535203682f, -0.14161228535203682f);
+  obj_fma2(p0, p1, z0, z1, 0.19985906672823953f, 0.19985906672823953f);
+  obj_fma2(p0, p1, z0, z1, -0.3333259702410447f, -0.3333259702410447f);
+  obj_fma2(p0, p1, z0, z1, 0.9999998863844667f, 0.9999998863844667f);
+  const float th0 = obj_theta(t0, p0, ad0, as0, d0, s0), th1 = obj_theta(t1, p1, ad1, as1, d1, s1);
+  float q0 = l0, q1 = l1, w0 = r0, w1 = r1;  // utils/dsp.py:413: sqrt(l*l + r*r), products rounded separately
+  obj_mul2(q0, q1, l0, l1);
+  obj_mul2(w0, w1, r0, r1);
+  obj_add2(q0, q1, w0, w1);
+  const float rad0 = __fsqrt_rn(q0), rad1 = __fsqrt_rn(q1);
+  float rt0 = rad0, rt1 = rad1;
+  obj_mul2(rt0, rt1, th0, th1);
+  obj_add2(a.sr[0], a.sr[1], rad0, rad1);
+  obj_add2(a.srt[0], a.srt[1], rt0, rt1);
+  float u0 = rt0, u1 = rt1;
+  obj_fma2(u0, u1, th0, th1, a.srt2[0], a.srt2[1]);
+  a.srt2[0] = u0;
+  a.srt2[1] = u1;
+  obj_mul2(rt0, rt1, th0, th1);
+  obj_fma2(rt0, rt1, th0, th1, a.srt3[0], a.srt3[1]);
+  a.srt3[0] = rt0;
+  a.srt3[1] = rt1;
+  float v0 = l0, v1 = l1;
+  obj_fma2(v0, v1, r0, r1, a.slr[0], a.slr[1]);
+  a.slr[0] = v0;
+  a.slr[1] = v1;
+  v0 = l0;
+  v1 = l1;
+  obj_fma2(v0, v1, l0, l1, a.sll[0], a.sll[1]);
+  a.sll[0] = v0;
+  a.sll[1] = v1;
+  // exact-enough ordering of the ratios by cross multiplication (ties keep the earlier frame)
+  if (s0 >= 0.0f) {
+    if (ad0 * a.s_pos > a.d_pos * as0) { a.d_pos = ad0; a.s_pos = as0; }
+  } else {
+    if (ad0 * a.s_neg > a.d_neg * as0) { a.d_neg = ad0; a.s_neg = as0; }
+  }
+  if (s1 >= 0.0f) {
+    if (ad1 * a.s_pos > a.d_pos * as1) { a.d_pos = ad1; a.s_pos = as1; }
+  } else {
+    if (ad1 * a.s_neg > a.d_neg * as1) { a.d_neg = ad1; a.s_neg = as1; }
   }
 }
 
@@ -121,27 +220,30 @@ __device__ __forceinline__ void run_candidate(const float* __restrict__ px, cons
     for (int k = 0; k < n_neg; ++k) {
       const float* q = px + tp[k];
 #pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = fsub(acc[r], q[32 * r]);
+      for (int r = 0; r < R; r += 2) obj_sub2(acc[r], acc[r + 1], q[32 * r], q[32 * r + 32]);
     }
     tp += n_neg;
     for (int k = 0; k < n_pos; ++k) {
       const float* q = px + tp[k];
 #pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = fadd(acc[r], q[32 * r]);
+      for (int r = 0; r < R; r += 2) obj_add2(acc[r], acc[r + 1], q[32 * r], q[32 * r + 32]);
     }
     tp += n_pos;
     if (apply_gain) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = fmul(acc[r], gain);
+      for (int r = 0; r < R; r += 2) obj_mul2(acc[r], acc[r + 1], gain, gain);
     }
 #pragma unroll
-    for (int r = 0; r < R; ++r) yv[r] = fadd(yv[r], acc[r]);
+    for (int r = 0; r < R; r += 2) obj_add2(yv[r], yv[r + 1], acc[r], acc[r + 1]);
   }
 }
 
 // Shared memory: float x0[TILE + halo] | float x1[TILE] | double acc[cand_per_group][OBJ_SLOTS]
 //                | int prog[warps][max_prog_words]
-__global__ void __launch_bounds__(OBJ_NT) vn_objective_kernel(const ObjParams p, int max_prog_words) {
+#ifndef VND_OBJ_MINB
+#define VND_OBJ_MINB 1
+#endif
+__global__ void __launch_bounds__(OBJ_NT, VND_OBJ_MINB) vn_objective_kernel(const ObjParams p, int max_prog_words) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int span = OBJ_TILE + p.halo;
   float* s0 = reinterpret_cast<float*>(smem_raw);
@@ -181,13 +283,34 @@ __global__ void __launch_bounds__(OBJ_NT) vn_objective_kernel(const ObjParams p,
       for (int i = lane; i < nprog; i += 32) myprog[i] = p.words[w0 + i];
       __syncwarp();
       LaneAcc a{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 1.f};
-      for (int base = 0; base < nvalid; base += 32 * OBJ_R) {
-        float yv[OBJ_R];
-        run_candidate<OBJ_R>(s0 + base + lane, myprog, p.apply_gain, yv);
+      if (nvalid == OBJ_TILE) {  // whole tile: no bounds checks, frames in packed pairs
+        LaneAcc2 b{{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, 0.f, 1.f, 0.f, 1.f};
+        for (int base = 0; base < OBJ_TILE; base += 32 * OBJ_R) {
+          float yv[OBJ_R];
+          run_candidate<OBJ_R>(s0 + base + lane, myprog, p.apply_gain, yv);
+          const float* r1 = s1 + base + lane;
 #pragma unroll
-        for (int r = 0; r < OBJ_R; ++r) {
-          const int i = base + lane + 32 * r;
-          if (i < nvalid) lane_acc_frame(a, yv[r], s1[i]);
+          for (int r = 0; r < OBJ_R; r += 2) lane_acc_pair(b, yv[r], yv[r + 1], r1[32 * r], r1[32 * r + 32]);
+        }
+        a.sr = b.sr[0] + b.sr[1];
+        a.srt = b.srt[0] + b.srt[1];
+        a.srt2 = b.srt2[0] + b.srt2[1];
+        a.srt3 = b.srt3[0] + b.srt3[1];
+        a.slr = b.slr[0] + b.slr[1];
+        a.sll = b.sll[0] + b.sll[1];
+        a.d_pos = b.d_pos;
+        a.s_pos = b.s_pos;
+        a.d_neg = b.d_neg;
+        a.s_neg = b.s_neg;
+      } else {
+        for (int base = 0; base < nvalid; base += 32 * OBJ_R) {
+          float yv[OBJ_R];
+          run_candidate<OBJ_R>(s0 + base + lane, myprog, p.apply_gain, yv);
+#pragma unroll
+          for (int r = 0; r < OBJ_R; ++r) {
+            const int i = base + lane + 32 * r;
+            if (i < nvalid) lane_acc_frame(a, yv[r], s1[i]);
+          }
         }
       }
       a.sr = warp_sum(a.sr);
