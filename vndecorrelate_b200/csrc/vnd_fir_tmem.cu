@@ -220,23 +220,31 @@ __device__ __forceinline__ void near_add(const float (&t)[kRG], float (&acc)[kRG
   }
 }
 
-// A tap served from shared memory.  `row` points at the staged block of this thread's row.  The
+// A tap served from shared memory.  `row` is the shared-memory address of the staged block of this thread's row.  The
 // operation word (build_ops) carries the word offset of the aligned 16-byte chunk that holds the
 // thread's first operand, the operand's position A inside it and kx, the number of chunks before the
 // run crosses into the next block, where the pitch inserts a 4-word gap (kx >= 9: no crossing).
 // The 32 operands lie in 8 (A == 0) or 9 chunks.
+// The chunks are read with explicit 16-byte loads: left to the compiler, the partly used first and last
+// chunk become 4- and 8-byte loads, which cost as many shared-memory wavefronts each as the full chunk
+// (lanes are 100 words apart: a 4-way conflict for LDS.32, 2-way for LDS.64) and up to twice together.
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 template <int A, bool SUB>
-__device__ __forceinline__ void far_tap_a(const float* __restrict__ row, int op, float (&acc)[kRG]) {
+__device__ __forceinline__ void far_tap_a(uint32_t row, int op, float (&acc)[kRG]) {
   constexpr int NC = (A == 0) ? 8 : 9;
-  const float4* p = reinterpret_cast<const float4*>(row + (op & 0xffff));
+  const uint32_t p = row + 4u * (uint32_t)(op & 0xffff);  // `row`: shared-memory address of the thread's row
   const int kx = (op >> 16) & 15;
   float4 c[NC];
   if (kx >= NC) {
 #pragma unroll
-    for (int k = 0; k < NC; ++k) c[k] = p[k];
+    for (int k = 0; k < NC; ++k) c[k] = lds128(p + 16u * k);
   } else {
 #pragma unroll
-    for (int k = 0; k < NC; ++k) c[k] = (k < kx ? p : p + 1)[k];
+    for (int k = 0; k < NC; ++k) c[k] = lds128(p + 16u * k + (k < kx ? 0u : 16u));
   }
   float t[NC * 4];
 #pragma unroll
@@ -264,7 +272,7 @@ __device__ __forceinline__ void far_tap_a(const float* __restrict__ row, int op,
 constexpr int kOpFar = (int)0x80000000u;
 
 template <bool SUB>
-__device__ __forceinline__ void far_tap(const float* __restrict__ row, int op, float (&acc)[kRG]) {
+__device__ __forceinline__ void far_tap(uint32_t row, int op, float (&acc)[kRG]) {
   switch ((op >> 24) & 3) {
     case 0: far_tap_a<0, SUB>(row, op, acc); break;
     case 1: far_tap_a<1, SUB>(row, op, acc); break;
@@ -275,7 +283,7 @@ __device__ __forceinline__ void far_tap(const float* __restrict__ row, int op, f
 
 // One tap: from tensor memory (op >= 0) or from shared memory.
 template <bool SUB, bool ALLFAR>
-__device__ __forceinline__ void one_tap(int op, uint32_t tcol0, const float* __restrict__ row, float (&acc)[kRG]) {
+__device__ __forceinline__ void one_tap(int op, uint32_t tcol0, uint32_t row, float (&acc)[kRG]) {
   if (!ALLFAR && op >= 0) {
     float t[kRG];
     near_issue(t, tcol0 + (uint32_t)op);
@@ -294,7 +302,7 @@ __device__ __forceinline__ void one_tap(int op, uint32_t tcol0, const float* __r
 // is loaded a whole tap before it is needed and never copied (a single loop-carried register made
 // ptxas copy the loaded word at once and stall on the shared-memory latency at every tap).
 template <bool SUB, bool ALLFAR>
-__device__ __forceinline__ void tap_list(const int* __restrict__ ops, int n, int nn, uint32_t tcol0, const float* __restrict__ row,
+__device__ __forceinline__ void tap_list(const int* __restrict__ ops, int n, int nn, uint32_t tcol0, uint32_t row,
                                          float (&acc)[kRG]) {
   if (n <= 0) return;
   int k = 0;
@@ -338,7 +346,7 @@ __device__ __forceinline__ void tap_list(const int* __restrict__ ops, int n, int
 // the positive list; acc *= gain; y += acc.
 template <bool ALLFAR>
 __device__ __forceinline__ void run_segments(const int* __restrict__ sprog, const int* __restrict__ segnear, int s0, int s1, const int*& ops,
-                                             int apply_gain, uint32_t tcol0, const float* __restrict__ row, float (&yv)[kRG]) {
+                                             int apply_gain, uint32_t tcol0, uint32_t row, float (&yv)[kRG]) {
   const int* seg = sprog + 1;
   for (int s = s0; s < s1; ++s) {
     const int n_neg = seg[3 * s], n_pos = seg[3 * s + 1];
@@ -591,7 +599,7 @@ __device__ __noinline__ void compute_main(const TmParams& P, uint32_t tbase, int
     const int S = sm.sprog[0];
     const int near_end = *sm.s_near_end;
     for (int ti = 0; ti < r.n_tiles; ++ti) {
-      const float* row = sm.in_all + b * sm.bufw + m * kPitch;
+      const uint32_t row = smem_u32(sm.in_all + b * sm.bufw + m * kPitch);
       float yv[kRG];
 #pragma unroll
       for (int rr = 0; rr < kRG; ++rr) yv[rr] = 0.0f;

@@ -238,16 +238,65 @@ __device__ __forceinline__ void run_candidate(const float* __restrict__ px, cons
   }
 }
 
-// Shared memory: float x0[TILE + halo] | float x1[TILE] | double acc[cand_per_group][OBJ_SLOTS]
-//                | int prog[warps][max_prog_words]
+// Whole tiles: a lane owns OBJ_R / 4 groups of FOUR CONSECUTIVE frames (frames base + 128 j + 4 lane + e),
+// and the filtered channel is staged four times, copy c shifted by c samples, so that every tap finds a
+// copy in which its operands are 16-byte aligned: one LDS.128 per group and tap instead of four LDS.32
+// (same shared-memory wavefronts, a quarter of the load instructions).  `dec` holds the program's taps
+// decoded once per candidate as word offsets (offset & 3) * span4 + (offset & ~3) into the copies.
+template <int R>
+__device__ __forceinline__ void run_candidate_v4(const float* __restrict__ px, const int* __restrict__ prog, const int* __restrict__ dec,
+                                                 int apply_gain, float (&yv)[R]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) yv[r] = 0.0f;
+  const int S = prog[0];
+  const int* seg = prog + 1;
+  const int* tp = dec;
+  for (int s = 0; s < S; ++s) {
+    const int n_neg = seg[3 * s], n_pos = seg[3 * s + 1];
+    const float gain = __int_as_float(seg[3 * s + 2]);
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.0f;
+    for (int k = 0; k < n_neg; ++k) {
+      const float4* q = reinterpret_cast<const float4*>(px + tp[k]);
+#pragma unroll
+      for (int j = 0; j < R / 4; ++j) {
+        const float4 v = q[32 * j];
+        obj_sub2(acc[4 * j], acc[4 * j + 1], v.x, v.y);
+        obj_sub2(acc[4 * j + 2], acc[4 * j + 3], v.z, v.w);
+      }
+    }
+    tp += n_neg;
+    for (int k = 0; k < n_pos; ++k) {
+      const float4* q = reinterpret_cast<const float4*>(px + tp[k]);
+#pragma unroll
+      for (int j = 0; j < R / 4; ++j) {
+        const float4 v = q[32 * j];
+        obj_add2(acc[4 * j], acc[4 * j + 1], v.x, v.y);
+        obj_add2(acc[4 * j + 2], acc[4 * j + 3], v.z, v.w);
+      }
+    }
+    tp += n_pos;
+    if (apply_gain) {
+#pragma unroll
+      for (int r = 0; r < R; r += 2) obj_mul2(acc[r], acc[r + 1], gain, gain);
+    }
+#pragma unroll
+    for (int r = 0; r < R; r += 2) obj_add2(yv[r], yv[r + 1], acc[r], acc[r + 1]);
+  }
+}
+
+// Shared memory: float x0[4][span4] (copy c = channel 0 shifted by c samples) | float x1[TILE] |
+//                double acc[cand_per_group][OBJ_SLOTS] | int prog[warps][max_prog_words] | int dec[warps][max_prog_words]
 #ifndef VND_OBJ_MINB
-#define VND_OBJ_MINB 1
+#define VND_OBJ_MINB 1  // CTAs per SM the register and shared-memory budgets are planned for (measured: 16 frames per lane in one CTA beats 8 in two)
 #endif
 __global__ void __launch_bounds__(OBJ_NT, VND_OBJ_MINB) vn_objective_kernel(const ObjParams p, int max_prog_words) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int span = OBJ_TILE + p.halo;
+  const int span4 = (span + 7) & ~3;  // words per shifted copy (a multiple of 4, room for the shift)
   float* s0 = reinterpret_cast<float*>(smem_raw);
-  float* s1 = s0 + span;
+  float* s1 = s0 + 4 * span4;
   double* acc = reinterpret_cast<double*>(s1 + OBJ_TILE);
   int* progs = reinterpret_cast<int*>(acc + (size_t)p.cand_per_group * OBJ_SLOTS);
 
@@ -259,6 +308,7 @@ __global__ void __launch_bounds__(OBJ_NT, VND_OBJ_MINB) vn_objective_kernel(cons
   const float* __restrict__ x0 = p.clips + (long long)clip * p.clip_stride;
   const float* __restrict__ x1 = x0 + p.chan_stride;
   int* myprog = progs + warp * max_prog_words;
+  int* mydec = progs + (kWarps + warp) * max_prog_words;
 
   for (int i = tid; i < ncand * OBJ_SLOTS; i += OBJ_NT) {
     const int slot = i % OBJ_SLOTS;
@@ -271,7 +321,13 @@ __global__ void __launch_bounds__(OBJ_NT, VND_OBJ_MINB) vn_objective_kernel(cons
     if (t0 >= p.frames) break;
     const long long remain = p.frames - t0;
     __syncthreads();  // previous tile fully consumed (also orders the acc init)
-    for (int i = tid; i < span; i += OBJ_NT) s0[i] = i < remain ? x0[t0 + i] : 0.0f;
+    for (int i = tid; i < span + 3; i += OBJ_NT) {  // copy c holds x0[t0 + c + j] at j
+      const float v = i < remain ? x0[t0 + i] : 0.0f;
+      if (i < span) s0[i] = v;
+      if (i >= 1 && i - 1 < span) s0[span4 + i - 1] = v;
+      if (i >= 2 && i - 2 < span) s0[2 * span4 + i - 2] = v;
+      if (i >= 3) s0[3 * span4 + i - 3] = v;
+    }
     for (int i = tid; i < OBJ_TILE; i += OBJ_NT) s1[i] = i < remain ? x1[t0 + i] : 0.0f;
     __syncthreads();
     const int nvalid = (int)(remain < OBJ_TILE ? remain : OBJ_TILE);
@@ -282,15 +338,27 @@ __global__ void __launch_bounds__(OBJ_NT, VND_OBJ_MINB) vn_objective_kernel(cons
       __syncwarp();
       for (int i = lane; i < nprog; i += 32) myprog[i] = p.words[w0 + i];
       __syncwarp();
+      {  // taps as word offsets into the shifted copies
+        const int ntap0 = 1 + 3 * myprog[0];
+        for (int i = ntap0 + lane; i < nprog; i += 32) {
+          const int off = myprog[i];
+          mydec[i - ntap0] = (off & 3) * span4 + (off & ~3);
+        }
+      }
+      __syncwarp();
       LaneAcc a{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 1.f};
       if (nvalid == OBJ_TILE) {  // whole tile: no bounds checks, frames in packed pairs
         LaneAcc2 b{{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, 0.f, 1.f, 0.f, 1.f};
         for (int base = 0; base < OBJ_TILE; base += 32 * OBJ_R) {
           float yv[OBJ_R];
-          run_candidate<OBJ_R>(s0 + base + lane, myprog, p.apply_gain, yv);
-          const float* r1 = s1 + base + lane;
+          run_candidate_v4<OBJ_R>(s0 + base + 4 * lane, myprog, mydec, p.apply_gain, yv);
+          const float4* r1 = reinterpret_cast<const float4*>(s1 + base + 4 * lane);
 #pragma unroll
-          for (int r = 0; r < OBJ_R; r += 2) lane_acc_pair(b, yv[r], yv[r + 1], r1[32 * r], r1[32 * r + 32]);
+          for (int j = 0; j < OBJ_R / 4; ++j) {
+            const float4 v = r1[32 * j];
+            lane_acc_pair(b, yv[4 * j], yv[4 * j + 1], v.x, v.y);
+            lane_acc_pair(b, yv[4 * j + 2], yv[4 * j + 3], v.z, v.w);
+          }
         }
         a.sr = b.sr[0] + b.sr[1];
         a.srt = b.srt[0] + b.srt[1];
@@ -438,9 +506,14 @@ static int plan_objective(long long frames, int n_clips, int n_cand, int halo, i
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
-  const size_t fixed = (size_t)(OBJ_TILE + halo + OBJ_TILE) * 4 + (size_t)(OBJ_NT / 32) * max_prog_words * 4 + 64;
-  if (fixed + OBJ_SLOTS * 8 * 16 > (size_t)kMaxDynSmem) return VND_EUNSUPPORTED;
-  int cpg = (int)(((size_t)kMaxDynSmem - fixed) / (OBJ_SLOTS * 8));
+  const size_t span4 = (size_t)((OBJ_TILE + halo + 7) & ~3);
+  const size_t fixed = (4 * span4 + OBJ_TILE) * 4 + (size_t)(OBJ_NT / 32) * 2 * max_prog_words * 4 + 64;
+  // VND_OBJ_MINB CTAs share the SM's 228 KB (1 KB of each is reserved by the system); a single CTA may take it all
+  size_t budget = (size_t)(233472 / VND_OBJ_MINB - 1024);
+  if (budget > (size_t)kMaxDynSmem) budget = (size_t)kMaxDynSmem;
+  if (fixed + OBJ_SLOTS * 8 * 16 > budget) budget = (size_t)kMaxDynSmem;  // long filters: one CTA per SM
+  if (fixed + OBJ_SLOTS * 8 * 16 > budget) return VND_EUNSUPPORTED;
+  int cpg = (int)((budget - fixed) / (OBJ_SLOTS * 8));
   if (cpg > n_cand) cpg = n_cand;
   if (cpg > 1024) cpg = 1024;
   const long long tiles = ceil_div<long long>(frames, OBJ_TILE);
