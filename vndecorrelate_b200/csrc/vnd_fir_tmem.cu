@@ -345,26 +345,30 @@ __device__ __forceinline__ void tap_list(const int* __restrict__ ops, int n, int
 // (decorrelation.py:402-414): acc = 0; acc -= x[n + i] over the negative list; acc += x[n + i] over
 // the positive list; acc *= gain; y += acc.
 template <bool ALLFAR>
-__device__ __forceinline__ void run_segments(const int* __restrict__ sprog, const int* __restrict__ segnear, int s0, int s1, const int*& ops,
-                                             int apply_gain, uint32_t tcol0, uint32_t row, float (&yv)[kRG]) {
-  const int* seg = sprog + 1;
+__device__ __forceinline__ void run_segments(const int4* __restrict__ segtab, int s0, int s1, const int*& ops, uint32_t tcol0, uint32_t row,
+                                             float (&yv)[kRG]) {
   for (int s = s0; s < s1; ++s) {
-    const int n_neg = seg[3 * s], n_pos = seg[3 * s + 1];
+    const int4 d = segtab[s];  // x = negative taps, y = positive taps, z = leading tensor-memory taps of both lists, w = gain bits
+    const int n_neg = d.x, n_pos = d.y;
     float acc[kRG];
 #pragma unroll
     for (int r = 0; r < kRG; ++r) acc[r] = 0.0f;
-    const int nn = ALLFAR ? 0 : segnear[s];  // leading tensor-memory taps: neg list in the low half, pos list in the high half
+    const int nn = ALLFAR ? 0 : d.z;  // leading tensor-memory taps: neg list in the low half, pos list in the high half
     tap_list<true, ALLFAR>(ops, n_neg, nn & 0xffff, tcol0, row, acc);
     tap_list<false, ALLFAR>(ops + n_neg, n_pos, nn >> 16, tcol0, row, acc);
     ops += n_neg + n_pos;
-    if (apply_gain) {
-      const float gain = __int_as_float(seg[3 * s + 2]);
+    {  // 1.0f when the program carries no gains (x * 1 == x bit for bit)
+      const float gain = __int_as_float(d.w);
 #pragma unroll
       for (int j = 0; j < kNP; ++j) mul2(acc[2 * j], acc[2 * j + 1], gain, gain);
     }
-    if (s == 0) {
+    if (s == 0) {  // the reference adds into zeros (a -0 partial sum becomes +0)
 #pragma unroll
-      for (int r = 0; r < kRG; ++r) yv[r] = fadd(acc[r], 0.0f);  // the reference adds into zeros
+      for (int j = 0; j < kNP; ++j) {
+        yv[2 * j] = acc[2 * j];
+        yv[2 * j + 1] = acc[2 * j + 1];
+        add2(yv[2 * j], yv[2 * j + 1], 0.0f, 0.0f);
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < kNP; ++j) add2(yv[2 * j], yv[2 * j + 1], acc[2 * j], acc[2 * j + 1]);
@@ -373,7 +377,7 @@ __device__ __forceinline__ void run_segments(const int* __restrict__ sprog, cons
 }
 
 // Dynamic shared memory: [0,112) mbarriers | [192,196) TMEM base | [196,200) first all-far segment |
-//   [256, ...) float in[3][nblk][100] | float stage[128][100] | int program[] | int ops[3][]
+//   [256, ...) float in[3][nblk][100] | float stage[128][100] | int program[] | int ops[3][] | int4 segtab[]
 // The role functions rebuild their pointers from this symbol so that every access stays in the
 // shared address space (LDS/STS, not generic loads).
 extern __shared__ __align__(128) unsigned char tm_smem[];
@@ -385,7 +389,7 @@ struct Smem {
   float* stage;
   int* sprog;
   int* ops;  // [3][opstride]: decoded tap operations per thread group
-  int* segnear;  // per segment: leading tensor-memory taps of the negative (low 16 bits) and positive list
+  int4* segtab;  // per segment: taps of the negative and positive list, their leading tensor-memory taps, gain bits
   int bufw;
   int opstride;
   __device__ __forceinline__ explicit Smem(const TmParams& P) {
@@ -397,7 +401,7 @@ struct Smem {
     sprog = reinterpret_cast<int*>(stage + kRows * kPitch);
     opstride = P.opstride;
     ops = sprog + opstride;
-    segnear = ops + kG * opstride;
+    segtab = reinterpret_cast<int4*>(ops + kG * opstride);  // opstride is a multiple of 4 words: 16-byte aligned
   }
 };
 
@@ -440,7 +444,7 @@ __device__ __forceinline__ bool begin_run(const TmParams& P, const Smem& sm, int
       int a = 0, b = 0;  // leading tensor-memory taps of the two lists
       while (a < n_neg && tq[a] <= kNearMax) ++a;
       while (n_neg + b < n && tq[n_neg + b] <= kNearMax) ++b;
-      sm.segnear[s] = a | (b << 16);
+      sm.segtab[s] = make_int4(n_neg, n - n_neg, a | (b << 16), p.apply_gain ? sm.sprog[3 + 3 * s] : __float_as_int(1.0f));
       tq += n;
     }
     *sm.s_near_end = ne;
@@ -583,7 +587,7 @@ __device__ __noinline__ void helper_main(const TmParams& P, uint32_t tbase, int 
 // ---------------------------------------------------------------- compute warp (q, g)
 __device__ __noinline__ void compute_main(const TmParams& P, uint32_t tbase, int tid) {
   const Smem sm(P);
-  const int n_runs = P.n_runs, apply_gain = P.f.apply_gain, stagger_ns = P.stagger_ns;  // P lives behind a generic pointer here
+  const int n_runs = P.n_runs, stagger_ns = P.stagger_ns;  // P lives behind a generic pointer here
   const int lane = tid & 31, warp = tid >> 5;
   const int q = warp & 3, g = warp >> 2;
   const int m = 32 * q + lane;
@@ -609,12 +613,12 @@ __device__ __noinline__ void compute_main(const TmParams& P, uint32_t tbase, int
       mbar_wait(&bars[B_TM_FULL + q], tpar);
       tmem_fence_after();
       VND_TRACE(ti, 1);
-      run_segments<false>(sm.sprog, sm.segnear, 0, near_end, ops, apply_gain, tcol0, row, yv);
+      run_segments<false>(sm.segtab, 0, near_end, ops, tcol0, row, yv);
       VND_TRACE(ti, 2);
       tmem_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_TM_FREE + q]);  // the helper may fill TMEM for the next tile
-      run_segments<true>(sm.sprog, sm.segnear, near_end, S, ops, apply_gain, tcol0, row, yv);
+      run_segments<true>(sm.segtab, near_end, S, ops, tcol0, row, yv);
       VND_TRACE(ti, 3);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_IN_FREE + b]);  // this warp is done with the tile buffer
@@ -679,7 +683,7 @@ __global__ void __launch_bounds__(kNT, 1) fir_tmem_kernel(const __grid_constant_
 // VND_TM_STAGGER_NS overrides the start-of-run delay between lane quarters (tuning).
 static const int g_stagger_ns = [] {
   const char* e = getenv("VND_TM_STAGGER_NS");
-  return e ? atoi(e) : 3000;
+  return e ? atoi(e) : 2000;
 }();
 
 // cuTensorMapEncodeTiled through the runtime (no link against libcuda).
@@ -717,9 +721,9 @@ int fir_tmem_launch(const FirParams& f, int max_prog_words, cudaStream_t st, lon
   if ((reinterpret_cast<uintptr_t>(f.y) % 16) != 0 || (f.y_sc % 4) != 0) return VND_EUNSUPPORTED;
   int nblk = kRows + (f.halo + 4 + kR - 1) / kR;
   if (nblk < kRows + 6) nblk = kRows + 6;  // the TMEM fill reads 512 columns of every row
-  const int opstride = max_prog_words + 4;
+  const int opstride = (max_prog_words + 4 + 3) & ~3;  // a multiple of 4 words: the segment table behind the lists stays 16-byte aligned
   const size_t bufw = ((size_t)nblk * kPitch + 31) & ~(size_t)31;
-  const size_t smem = kBarBytes + kNBuf * bufw * 4 + (size_t)kRows * kPitch * 4 + (size_t)(2 + kG) * opstride * 4;
+  const size_t smem = kBarBytes + kNBuf * bufw * 4 + (size_t)kRows * kPitch * 4 + (size_t)(3 + kG) * opstride * 4;
   if (smem > (size_t)kMaxDynSmem || nblk > 256) return VND_EUNSUPPORTED;  // a TMA box has at most 256 rows
   if (f.channels > 1 && (f.x_sc % 4 != 0 || f.x_sc < f.frames || f.y_sc < f.frames)) return VND_EUNSUPPORTED;
   const long long span = (long long)nblk * kR;  // samples a tile's bulk loads touch
