@@ -43,6 +43,11 @@
 #include "vnd_common.cuh"
 #include "vnd_fir.cuh"
 
+#ifndef VND_TM_POLL_NS
+#define VND_TM_POLL_NS 200  // sleep of a data-movement lane between two polls of an mbarrier
+#endif
+#define VND_STR2(x) #x
+#define VND_STR(x) VND_STR2(x)
 #ifndef VND_TM_RUN_MAX
 #define VND_TM_RUN_MAX 512  // most consecutive tiles of one channel in a CTA run
 #endif
@@ -147,7 +152,7 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
       "WAIT_%=:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra DONE_%=;\n"
-      "nanosleep.u32 200;\n"
+      "nanosleep.u32 " VND_STR(VND_TM_POLL_NS) ";\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
       "}\n" ::"r"(bar),
