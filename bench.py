@@ -306,7 +306,7 @@ def run_b200(args) -> None:
         kernel_name = "fir_tile_kernel<float,SEGMENTED>"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": kernel_name, "kernel_ms": kernel_ms, "peak_source": peak_src,
-                "note": "HBM is not the binding resource: every (output, tap) pair moves one word from on-chip memory to a register and costs one add; the kernel is bound by instruction issue and on-chip latency (ncu: issue slots ~56 % busy, shared-memory pipe ~32 %, DRAM ~17 %). See DESIGN.md section 4 and profiles/r01_summary.md"}
+                "note": "HBM is not the binding resource: every (output, tap) pair moves one word from on-chip memory to a register and costs one add; the kernel is bound by the shared-memory pipe and on-chip latency (ncu: shared-memory pipe ~67 % busy, issue slots ~57 %, DRAM ~35 %). See DESIGN.md section 4 and profiles/r01_summary.md"}
 
     # end to end through the C ABI with HOST buffers (copies inside the timed region)
     e2e = None
