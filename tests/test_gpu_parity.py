@@ -511,3 +511,70 @@ def test_batched_refinement_equals_one_at_a_time(api):
         minima, taus, grid, lambda t: OPT.symmetry_aware_objective(sig, api.HaasEffect(sample_rate_hz=fs, delay_time_seconds=t, mode="LR"), **kw))
     batched = OPT.optimize_haas_delay(input_signal=sig, sample_rate_hz=fs, max_delay_seconds=0.03, grid_size=grid)
     assert batched == one_at_a_time
+
+
+# ------------------------------------------------------------------ numpy-order sum of squares (rms_normalize, utils/dsp.py:107-109)
+def _colsumsq(t):
+    """vnd_colsumsq_seq_f32_dev on a (frames, channels) CUDA tensor -> float32 sums per column."""
+    import ctypes as C
+
+    import torch
+
+    from vndecorrelate_b200 import _native as N
+    from vndecorrelate_b200 import runtime as R
+
+    sig = R.torch_signal(t)
+    out = torch.empty(t.shape[1], dtype=torch.float32, device=t.device)
+    rc = N.lib().vnd_colsumsq_seq_f32_dev(C.byref(sig), C.c_void_p(out.data_ptr()), C.c_void_p(R.torch_stream_ptr(t)))
+    assert rc == 0, N.lib().vnd_last_error()
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def _seq_columns(rng, kind, frames):
+    if kind == "audio":  # what rms_normalize sees
+        return (rng.standard_normal((frames, 3)) * 0.2).astype(np.float32)
+    if kind == "range":  # 30 decades of dynamic range: many binade changes, addends far below one ulp of the sum
+        return (rng.standard_normal((frames, 3)) * 10.0 ** rng.uniform(-15, 4, (frames, 3))).astype(np.float32)
+    if kind == "ties":  # squares that are small multiples of a power of two: exact ties against the running sum's ulp
+        k = rng.integers(0, 64, (frames, 3)).astype(np.float32)
+        x = np.sqrt(k * np.float32(2.0 ** -20)).astype(np.float32)
+        x[rng.random((frames, 3)) < 0.3] = np.float32(2.0 ** -13)  # square 2^-26: half an ulp once the sum passes 2^-2
+        x[0, :] = np.float32(0.5)
+        return x
+    if kind == "silence":  # zeros, then subnormal squares, then signal
+        x = np.zeros((frames, 3), dtype=np.float32)
+        x[frames // 3: frames // 2] = np.float32(1e-21) * rng.standard_normal((frames // 2 - frames // 3, 3)).astype(np.float32)
+        x[frames // 2:] = (rng.standard_normal((frames - frames // 2, 3)) * 1e-3).astype(np.float32)
+        return x
+    if kind == "huge":  # overflow to inf on the way
+        x = (rng.standard_normal((frames, 3)) * 1e17).astype(np.float32)
+        x[:, 1] *= np.float32(100.0)
+        return x
+    if kind == "nan":
+        x = (rng.standard_normal((frames, 3)) * 0.1).astype(np.float32)
+        x[frames // 2, 0] = np.nan
+        x[frames // 3, 1] = np.inf
+        return x
+    raise AssertionError(kind)
+
+
+@pytest.mark.parametrize("kind", ["audio", "range", "ties", "silence", "huge", "nan"])
+@pytest.mark.parametrize("frames", [4095, 4096, 8191, 8192, 8193, 100003, 407077])
+def test_sequential_sum_of_squares_is_numpy_order(kind, frames):
+    """The parallel evaluation (transducer scan per binade, vnd_post.cu) returns the strict left-to-right
+    float32 running sum bit for bit, like the scalar chain it replaces for long signals."""
+    import torch
+
+    rng = np.random.default_rng(frames * 7 + len(kind))
+    x = _seq_columns(rng, kind, frames)
+    with np.errstate(over="ignore", invalid="ignore"):
+        want = np.array([O.seq_sumsq_f32(x[:, c]) for c in range(x.shape[1])], dtype=np.float32)
+    got = _colsumsq(torch.from_numpy(x).cuda())
+    assert got.dtype == np.float32
+    # NaN results compare as NaN (the payload of an arithmetic NaN is the hardware's), everything else bit for bit
+    same = (lambda a, b: np.array_equal(a, b, equal_nan=True)) if kind == "nan" else G.same_bits
+    assert same(got, want), (kind, frames, got, want)
+    # a strided view (every second column of a wider slab) reads the same values
+    wide = torch.from_numpy(np.repeat(x, 2, axis=1)).cuda()
+    assert same(_colsumsq(wide[:, ::2]), want)

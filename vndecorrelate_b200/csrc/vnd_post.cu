@@ -8,6 +8,8 @@
 //   apply_stereo_width           src/vndecorrelate/utils/dsp.py:21-37
 //   encode_signal_to_side_channel src/vndecorrelate/utils/dsp.py:40-63
 
+#include <stdlib.h>
+
 #include "vnd_common.cuh"
 
 namespace vnd {
@@ -90,6 +92,199 @@ __global__ void __launch_bounds__(256) seq_sumsq_kernel(const SeqParams p) {
     }
   }
   if (tid == 0) reinterpret_cast<T*>(p.sums)[col] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same strict left-to-right float32 running sum, evaluated in parallel and still bit for bit.
+//
+// While the running sum s stays inside one binade [2^e, 2^(e+1)) its ulp u = 2^(e-23) is fixed, s = n u
+// with an integer n in [2^23, 2^24), and adding a >= 0 is integer arithmetic: with a / u = q + f,
+//     fl(s + a) / u = n + q + r,   r = [f > 1/2], and for the tie f == 1/2:  r = (n + q) & 1
+// (round half to even looks at the parity of the significand, i.e. of n + q).  So every addend is a tiny
+// transducer on the parity of n: (increment if n is even, increment if n is odd), both known from a and e
+// alone, and transducers compose associatively:  (A then B)[p] = A[p] + B[(p + A[p]) & 1].  A CTA scans
+// 8192 addends at once: each thread composes its 8 consecutive elements, a block-wide exclusive scan
+// gives every thread the state at its first element, and the thread then walks its elements with the
+// real parity.  Subnormal sums and the first normal binade share the grid u = 2^-149 (n = the bit
+// pattern of s), so zeros and silence need no special case.
+// The assumption "s stays in the binade" is checked, not trusted: the first element whose result reaches
+// 2^24 ulps (the rounding grid changes there) is found by the walk, everything before it is committed,
+// that one addition is done with the real float32 add, and the scan restarts behind it in the new
+// binade - about 30 times per signal, since the sum only grows.  Increments saturate at 2^26 ulps (they
+// only matter below 2^24); inf / NaN addends or sums fall back to the scalar chain for the rest.
+// ------------------------------------------------------------------------------------------------
+#ifndef VND_PS_E
+#define VND_PS_E 8
+#endif
+#ifndef VND_PS_NT
+#define VND_PS_NT 1024
+#endif
+constexpr int PS_NT = VND_PS_NT, PS_E = VND_PS_E, PS_B = PS_NT * PS_E;
+constexpr unsigned PS_SAT = 1u << 26, PS_TOP = 1u << 24;
+#ifndef VND_PS_HEAD
+#define VND_PS_HEAD 4096
+#endif
+constexpr int PS_HEAD = VND_PS_HEAD;  // addends chained by one thread before the scans start
+
+struct Tr {
+  unsigned d0, d1;  // increment of n for an even / odd n
+};
+__device__ __forceinline__ Tr tr_compose(Tr a, Tr b) {  // a first, then b
+  Tr r;
+  r.d0 = umin(a.d0 + ((a.d0 & 1u) ? b.d1 : b.d0), PS_SAT);
+  r.d1 = umin(a.d1 + ((a.d1 & 1u) ? b.d0 : b.d1), PS_SAT);
+  return r;
+}
+// transducer of the addend a (>= 0) for a running sum with ulp u: t = a / u is formed exactly by two
+// multiplications with powers of two, sc1 * sc2 = 1 / u (an underflowing t is far below 1/2 and rounds to an
+// increment of 0 either way; an overflowing one saturates, as do inf and NaN: they force the real addition)
+__device__ __forceinline__ Tr tr_of(float a, float sc1, float sc2) {
+  const float t = fmul(fmul(a, sc1), sc2);
+  if (!(t < 67108864.0f)) return Tr{PS_SAT, PS_SAT};  // >= 2^26 ulps, inf, NaN
+  const unsigned q = (unsigned)t;              // floor (t >= 0)
+  const float f = fsub(t, (float)q);           // exact: t has at most 24 significant bits
+  const unsigned up = f > 0.5f ? 1u : 0u, tie = f == 0.5f ? 1u : 0u;
+  return Tr{q + (up | (tie & q & 1u)), q + (up | (tie & (q + 1u) & 1u))};  // tie: to the even significand
+}
+
+static_assert(PS_NT == 1024, "the scan of the warp totals assumes 32 warps");
+__global__ void __launch_bounds__(PS_NT) seq_sumsq_par_kernel(const SeqParams p) {
+  __shared__ float stage[PS_HEAD];  // the head's addends
+  __shared__ Tr warp_tot[PS_NT / 32];
+  __shared__ unsigned sh_cross, sh_n;
+  __shared__ float sh_a, sh_s;
+  const int col = blockIdx.x;
+  const float* base;
+  long long st;
+  if (col < p.channels) {
+    base = reinterpret_cast<const float*>(p.a) + (long long)col * p.a_sc;
+    st = p.a_st;
+  } else {
+    base = reinterpret_cast<const float*>(p.b) + (long long)(col - p.channels) * p.b_sc;
+    st = p.b_st;
+  }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long N = p.frames;
+  float s = 0.0f;
+  long long pos = 0;
+  {  // The sum changes binade at about every doubling of the position: the first PS_HEAD addends would cost a
+     // round each time.  They are staged by everybody and chained by one thread (4 clocks per addend).
+    float* head = stage;
+    const int nh = (int)(N < PS_HEAD ? N : PS_HEAD);
+    for (int i = tid; i < nh; i += PS_NT) head[i] = sq<float>(base[(long long)i * st]);
+    __syncthreads();
+    if (tid == 0) {
+      float h = 0.0f;
+      for (int i = 0; i < nh; ++i) h = fadd(h, head[i]);
+      sh_s = h;
+    }
+    __syncthreads();
+    s = sh_s;
+    pos = nh;
+  }
+  while (pos < N) {
+    const unsigned sb = __float_as_uint(s);
+    const unsigned seb = sb >> 23;
+    if (seb >= 255u) {  // inf or NaN so far: the scalar chain finishes the column
+      if (tid == 0) {
+        for (long long t = pos; t < N; ++t) s = fadd(s, sq<float>(base[t * st]));
+        sh_s = s;
+      }
+      __syncthreads();
+      s = sh_s;
+      break;
+    }
+    const int e = seb ? (int)seb - 127 : -126;
+    const unsigned n_in = seb ? ((sb & 0x7fffffu) | 0x800000u) : sb;
+    const int k = 23 - e, k1 = k / 2;  // 1 / u = 2^k as the product of two representable powers of two (k in [-104, 149])
+    const float sc1 = __uint_as_float((unsigned)(127 + k1) << 23), sc2 = __uint_as_float((unsigned)(127 + k - k1) << 23);
+    if (tid == 0) sh_cross = PS_B;
+    // this thread's PS_E consecutive addends (zeros behind the end: they change nothing)
+    float a[PS_E];
+    Tr el[PS_E];
+    Tr loc{0u, 0u};
+    // (staging the round coalesced through shared memory was measured slower than these strided loads: the
+    // lines stay in L1 across a thread's PS_E loads)
+    const long long t0 = pos + (long long)tid * PS_E;
+#pragma unroll
+    for (int j = 0; j < PS_E; ++j) a[j] = (t0 + j < N) ? sq<float>(base[(t0 + j) * st]) : 0.0f;
+#pragma unroll
+    for (int j = 0; j < PS_E; ++j) {
+      el[j] = tr_of(a[j], sc1, sc2);
+      loc = tr_compose(loc, el[j]);
+    }
+    // block-wide exclusive scan of the thread transducers (lower threads first)
+    Tr inc = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      Tr up;
+      up.d0 = __shfl_up_sync(0xffffffffu, inc.d0, o);
+      up.d1 = __shfl_up_sync(0xffffffffu, inc.d1, o);
+      if (lane >= o) inc = tr_compose(up, inc);
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      Tr w = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        Tr up;
+        up.d0 = __shfl_up_sync(0xffffffffu, w.d0, o);
+        up.d1 = __shfl_up_sync(0xffffffffu, w.d1, o);
+        if (lane >= o) w = tr_compose(up, w);
+      }
+      warp_tot[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    Tr pre{0u, 0u};  // everything before this thread
+    {
+      Tr lanes_before;
+      lanes_before.d0 = __shfl_up_sync(0xffffffffu, inc.d0, 1);
+      lanes_before.d1 = __shfl_up_sync(0xffffffffu, inc.d1, 1);
+      if (lane == 0) lanes_before = Tr{0u, 0u};
+      pre = warp > 0 ? tr_compose(warp_tot[warp - 1], lanes_before) : lanes_before;
+    }
+    // walk the own elements with the real parity; find the first one that leaves the binade
+    unsigned n = n_in + ((n_in & 1u) ? pre.d1 : pre.d0);
+    unsigned nv[PS_E];
+    int cross = -1;
+    if (n < PS_TOP) {
+#pragma unroll
+      for (int j = 0; j < PS_E; ++j) {
+        const unsigned nn = n + ((n & 1u) ? el[j].d1 : el[j].d0);
+        if (cross < 0) {
+          if (nn >= PS_TOP) cross = j;
+          else n = nn;
+        }
+        nv[j] = n;
+      }
+      if (cross >= 0) atomicMin(&sh_cross, (unsigned)(tid * PS_E + cross));
+    }
+    __syncthreads();
+    const unsigned c = sh_cross;  // elements committed in this binade; element c (if < PS_B) takes the real addition
+    if (c > 0u && (int)((c - 1u) / PS_E) == tid) {  // static indices: a run-time subscript would put nv[] in local memory
+      const int idx = (int)((c - 1u) % PS_E);
+#pragma unroll
+      for (int j = 0; j < PS_E; ++j)
+        if (j == idx) sh_n = nv[j];
+    }
+    if (c < (unsigned)PS_B && (int)(c / PS_E) == tid) {
+      const int idx = (int)(c % PS_E);
+#pragma unroll
+      for (int j = 0; j < PS_E; ++j)
+        if (j == idx) sh_a = a[j];
+    }
+    __syncthreads();
+    if (c > 0u) s = __uint_as_float(((unsigned)(e + 126) << 23) + sh_n);
+    pos += c;
+    if (c < (unsigned)PS_B) {
+      s = fadd(s, sh_a);
+      pos += 1;
+    }
+    // no barrier here: the next round rewrites sh_cross only after every thread has read it (the barrier
+    // above), and sh_n / sh_a / warp_tot only behind barriers that every thread reaches after its reads
+  }
+  if (tid == 0) reinterpret_cast<float*>(p.sums)[col] = s;
 }
 
 // gains[c] = sqrt(mean_x[c]) / sqrt(mean_y[c] + eps) with numpy's dtype chain: the mean divides in
@@ -321,8 +516,13 @@ int seq_sumsq_launch(const vnd_signal* a, const vnd_signal* b, void* sums, cudaS
     cols *= 2;
   }
   if (cols == 0) return VND_OK;
+  static const bool serial_only = [] {
+    const char* e = getenv("VND_SEQSUM_SERIAL");  // testing: the scalar chain for every length
+    return e && e[0] == '1';
+  }();
   if (a->dtype == VND_F64) seq_sumsq_kernel<double><<<cols, 256, 0, st>>>(p);
-  else seq_sumsq_kernel<float><<<cols, 256, 0, st>>>(p);
+  else if (serial_only || a->frames < 4096) seq_sumsq_kernel<float><<<cols, 256, 0, st>>>(p);
+  else seq_sumsq_par_kernel<<<cols, PS_NT, 0, st>>>(p);
   return after_launch("seq_sumsq_kernel");
 }
 
