@@ -317,7 +317,7 @@ def run_b200(args) -> None:
         sub = prog.slice_channels(0, Ce)
         hs = sub.host_struct()
         ctx = R.HostContext.get(local_rank)
-        chunk = max(1, Ce // 8)
+        chunk = max(1, Ce // max(1, args.e2e_chunks))  # channels per pipeline stage: more stages = shorter fill and drain
 
         def e2e_step():
             N.check(lib.vnd_sparse_fir_stream_host(ctx.handle, hx.array.ctypes.data, hy.array.ctypes.data, L, Ce, C.byref(hs), chunk), "vnd_sparse_fir_stream_host")
@@ -371,6 +371,7 @@ def main() -> None:
     ap.add_argument("--channels-per-gpu", type=int, default=CHANNELS_PER_GPU)
     ap.add_argument("--frames", type=int, default=FRAMES)
     ap.add_argument("--e2e-channels", type=int, default=32)
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="pipeline stages of the end-to-end call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
