@@ -371,7 +371,7 @@ def main() -> None:
     ap.add_argument("--channels-per-gpu", type=int, default=CHANNELS_PER_GPU)
     ap.add_argument("--frames", type=int, default=FRAMES)
     ap.add_argument("--e2e-channels", type=int, default=32)
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="pipeline stages of the end-to-end call")
+    ap.add_argument("--e2e-chunks", type=int, default=32, help="pipeline stages of the end-to-end call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
