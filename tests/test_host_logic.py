@@ -351,3 +351,23 @@ def test_lockstep_minimize_propagates_errors():
 
     with pytest.raises(ValueError, match="boom"):
         lockstep_minimize([(0.0, 1.0), (1.0, 2.0)], bad)
+
+
+def test_pinned_output_pool_falls_back_without_a_device():
+    """runtime.pinned_empty backs small results by page-locked memory; without a CUDA device (this container) the
+    allocation fails and it must hand out an ordinary array and leave the pool's accounting untouched."""
+    from vndecorrelate_b200 import runtime as R
+
+    before = R._POOL_BYTES[0]
+    a = R.pinned_empty((100, 2), np.float64)
+    assert a.shape == (100, 2) and a.dtype == np.float64 and a.flags.writeable
+    a[:] = 1.0
+    try:
+        import torch
+
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        assert R._POOL_BYTES[0] == before
+    assert R.pinned_empty((0, 2), np.float32).shape == (0, 2)

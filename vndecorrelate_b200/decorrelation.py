@@ -126,7 +126,7 @@ def _vn_decorrelate(x32, program: TapProgram, *, num_outs: int, ms_encode: bool,
                                                R.torch_stream_ptr(x32)), "vnd_vn_decorrelate_dev")
         return out
     xa = R.dense(x32)
-    out = np.empty((frames + haas_delay, num_outs), dtype=np.float64 if out_f64 else np.float32)
+    out = R.pinned_empty((frames + haas_delay, num_outs), np.float64 if out_f64 else np.float32)
     sx = R.host_signal(xa, mono_as_stereo=mono)
     so = R.host_signal(out)
     ps = program.host_struct()

@@ -130,6 +130,68 @@ def device_program(prog, device):
 # ---------------------------------------------------------------------------------------------
 
 
+class _PinnedBlock:
+    """One page-locked block of the output pool; goes back to the pool when the last array on it dies."""
+
+    __slots__ = ("ptr", "nbytes", "__weakref__")
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.ptr, self.nbytes = ptr, nbytes
+
+    def __del__(self):
+        _pinned_pool_release(self.ptr, self.nbytes)
+
+
+_POOL_LOCK = threading.Lock()
+_POOL_FREE: dict[int, list[int]] = {}   # block size -> free pointers
+_POOL_BYTES = [0]                       # page-locked bytes this pool has allocated
+_POOL_CAP = int(os.environ.get("VND_PINNED_POOL_MB", "512")) << 20
+_POOL_MAX_BLOCK = 128 << 20
+
+
+def _pinned_pool_release(ptr: int, nbytes: int) -> None:
+    try:
+        with _POOL_LOCK:
+            _POOL_FREE.setdefault(nbytes, []).append(ptr)
+    except Exception:  # interpreter shutdown
+        pass
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """``np.empty(shape, dtype)`` on page-locked memory from a recycling pool, so that the device-to-host copy of
+    a result is one DMA at link speed instead of a staged copy into freshly mapped pages (which costs more
+    than the kernels for the stereo files of BASELINE configs 1 and 2).  The array owns its block: it returns
+    to the pool when the array and its views are gone.  Falls back to ``np.empty`` for very large results or
+    when the pool is at its cap (``VND_PINNED_POOL_MB``, default 512)."""
+    dt = np.dtype(dtype)
+    count = int(np.prod(shape))
+    nbytes = count * dt.itemsize
+    if nbytes == 0 or nbytes > _POOL_MAX_BLOCK:
+        return np.empty(shape, dtype=dt)
+    size = 1 << max(16, (nbytes - 1).bit_length())  # power-of-two blocks of at least 64 KB
+    ptr = None
+    with _POOL_LOCK:
+        free = _POOL_FREE.get(size)
+        if free:
+            ptr = free.pop()
+        elif _POOL_BYTES[0] + size <= _POOL_CAP:
+            _POOL_BYTES[0] += size
+        else:
+            return np.empty(shape, dtype=dt)
+    if ptr is None:
+        p = C.c_void_p()
+        rc = N.lib().vnd_host_alloc(size, C.byref(p))
+        if rc != 0 or not p.value:
+            with _POOL_LOCK:
+                _POOL_BYTES[0] -= size
+            return np.empty(shape, dtype=dt)
+        ptr = p.value
+    block = _PinnedBlock(ptr, size)
+    buf = (C.c_char * size).from_address(ptr)
+    buf._vnd_block = block  # the ctypes view keeps the block alive, numpy keeps the ctypes view alive
+    return np.frombuffer(buf, dtype=dt, count=count).reshape(shape)
+
+
 class PinnedArray:
     """A numpy view of page-locked host memory from ``vnd_host_alloc``."""
 
