@@ -26,7 +26,10 @@
 namespace vnd {
 
 constexpr int OBJ_SLOTS = 12;  // doubles per (clip, candidate) partial, see vnd_b200.h
-constexpr int OBJ_NT = 512;
+#ifndef VND_OBJ_NT
+#define VND_OBJ_NT 640  // 20 warps: measured best of 512 / 640 / 768 / 896 / 1024 threads (16 frames per lane)
+#endif
+constexpr int OBJ_NT = VND_OBJ_NT;
 #ifndef VND_OBJ_R
 #define VND_OBJ_R 16
 #endif

@@ -95,7 +95,7 @@ def _sparse_fir(x, program: TapProgram, num_outs: int):
     xa = R.dense(_fir_compute_array(np.asarray(x)))
     frames = xa.shape[0]
     planar = xa.ndim == 2 and xa.shape[1] > 1 and not xa.flags.c_contiguous
-    y = np.empty((num_outs, frames), dtype=np.float32).T if planar else np.empty((frames, num_outs), dtype=np.float32)
+    y = R.pinned_empty((num_outs, frames), np.float32).T if planar else R.pinned_empty((frames, num_outs), np.float32)
     sx, sy = R.host_signal(xa), R.host_signal(y)
     ps = program.host_struct()
     N.check(lib.vnd_sparse_fir_host(R.HostContext.get().handle, C.byref(sx), C.byref(sy), C.byref(ps)), "vnd_sparse_fir_host")
@@ -150,7 +150,7 @@ def _haas(x32, *, delay: int, delayed_channel: int, mode_ms: bool, width):
             N.check(lib.vnd_haas_dev(C.byref(sx), C.byref(so), *args, R.torch_stream_ptr(x32)), "vnd_haas_dev")
         return out
     xa = R.dense(x32)
-    out = np.empty((frames + delay, 2), dtype=np.float64)
+    out = R.pinned_empty((frames + delay, 2), np.float64)
     sx, so = R.host_signal(xa, mono_as_stereo=mono), R.host_signal(out)
     N.check(lib.vnd_haas_host(R.HostContext.get().handle, C.byref(sx), C.byref(so), *args), "vnd_haas_host")
     return out
