@@ -8,6 +8,7 @@
 //   apply_stereo_width           src/vndecorrelate/utils/dsp.py:21-37
 //   encode_signal_to_side_channel src/vndecorrelate/utils/dsp.py:40-63
 
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 #include "vnd_common.cuh"
@@ -287,6 +288,171 @@ __global__ void __launch_bounds__(PS_NT) seq_sumsq_par_kernel(const SeqParams p)
   if (tid == 0) reinterpret_cast<float*>(p.sums)[col] = s;
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same scan over a thread-block CLUSTER: PS_K CTAs (one SM each) share a column, a round covers
+// PS_K x 8192 addends, and the CTAs exchange three words per round through distributed shared memory
+// (their composed transducer, their first binade change, the committed sum), each exchange closed by a
+// cluster barrier.  Every CTA keeps its own copy of the running sum and position, so the control flow is
+// identical everywhere; the head and the inf / NaN tail are computed redundantly (no communication).
+// ------------------------------------------------------------------------------------------------
+#ifndef VND_PS_K
+#define VND_PS_K 8
+#endif
+constexpr int PS_K = VND_PS_K;
+constexpr unsigned PS_BK = (unsigned)PS_K * PS_B;  // addends per round
+
+namespace cg = cooperative_groups;
+
+__global__ void __cluster_dims__(PS_K, 1, 1) __launch_bounds__(PS_NT) seq_sumsq_cluster_kernel(const SeqParams p) {
+  __shared__ float stage[PS_HEAD];
+  __shared__ Tr warp_tot[PS_NT / 32];
+  __shared__ Tr cta_tot[PS_K];        // written by every CTA of the cluster (slot = its rank)
+  __shared__ unsigned cta_min[PS_K];  // likewise: first binade change each CTA found (PS_BK = none)
+  __shared__ unsigned sh_cross, sh_n;
+  __shared__ float sh_a, sh_s;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
+  const int col = blockIdx.x / PS_K;
+  const float* base;
+  long long st;
+  if (col < p.channels) {
+    base = reinterpret_cast<const float*>(p.a) + (long long)col * p.a_sc;
+    st = p.a_st;
+  } else {
+    base = reinterpret_cast<const float*>(p.b) + (long long)(col - p.channels) * p.b_sc;
+    st = p.b_st;
+  }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long N = p.frames;
+  float s = 0.0f;
+  long long pos = 0;
+  {  // head: chained by one thread of every CTA (same result everywhere)
+    const int nh = (int)(N < PS_HEAD ? N : PS_HEAD);
+    for (int i = tid; i < nh; i += PS_NT) stage[i] = sq<float>(base[(long long)i * st]);
+    __syncthreads();
+    if (tid == 0) {
+      float h = 0.0f;
+      for (int i = 0; i < nh; ++i) h = fadd(h, stage[i]);
+      sh_s = h;
+    }
+    __syncthreads();
+    s = sh_s;
+    pos = nh;
+  }
+  while (pos < N) {
+    const unsigned sb = __float_as_uint(s);
+    const unsigned seb = sb >> 23;
+    if (seb >= 255u) {  // inf or NaN so far: the scalar chain finishes the column (in every CTA alike)
+      if (tid == 0) {
+        for (long long t = pos; t < N; ++t) s = fadd(s, sq<float>(base[t * st]));
+        sh_s = s;
+      }
+      __syncthreads();
+      s = sh_s;
+      break;
+    }
+    const int e = seb ? (int)seb - 127 : -126;
+    const unsigned n_in = seb ? ((sb & 0x7fffffu) | 0x800000u) : sb;
+    const int k = 23 - e, k1 = k / 2;
+    const float sc1 = __uint_as_float((unsigned)(127 + k1) << 23), sc2 = __uint_as_float((unsigned)(127 + k - k1) << 23);
+    if (tid == 0) sh_cross = PS_BK;
+    float a[PS_E];
+    Tr el[PS_E];
+    Tr loc{0u, 0u};
+    const unsigned g0 = (rank * (unsigned)PS_NT + (unsigned)tid) * (unsigned)PS_E;  // index of the thread's first addend in the round
+    const long long t0 = pos + (long long)g0;
+#pragma unroll
+    for (int j = 0; j < PS_E; ++j) a[j] = (t0 + j < N) ? sq<float>(base[(t0 + j) * st]) : 0.0f;
+#pragma unroll
+    for (int j = 0; j < PS_E; ++j) {
+      el[j] = tr_of(a[j], sc1, sc2);
+      loc = tr_compose(loc, el[j]);
+    }
+    Tr inc = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      Tr up;
+      up.d0 = __shfl_up_sync(0xffffffffu, inc.d0, o);
+      up.d1 = __shfl_up_sync(0xffffffffu, inc.d1, o);
+      if (lane >= o) inc = tr_compose(up, inc);
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      Tr w = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        Tr up;
+        up.d0 = __shfl_up_sync(0xffffffffu, w.d0, o);
+        up.d1 = __shfl_up_sync(0xffffffffu, w.d1, o);
+        if (lane >= o) w = tr_compose(up, w);
+      }
+      warp_tot[lane] = w;
+      const Tr tot = Tr{__shfl_sync(0xffffffffu, w.d0, 31), __shfl_sync(0xffffffffu, w.d1, 31)};
+      if (lane < PS_K) *cluster.map_shared_rank(&cta_tot[rank], lane) = tot;  // lane r tells CTA r this CTA's composed transducer
+    }
+    cluster.sync();  // also the CTA barrier behind the scan of the warp totals
+    Tr pre{0u, 0u};
+    for (unsigned r = 0; r < rank; ++r) pre = tr_compose(pre, cta_tot[r]);  // the CTAs before this one
+    {
+      Tr lanes_before;
+      lanes_before.d0 = __shfl_up_sync(0xffffffffu, inc.d0, 1);
+      lanes_before.d1 = __shfl_up_sync(0xffffffffu, inc.d1, 1);
+      if (lane == 0) lanes_before = Tr{0u, 0u};
+      if (warp > 0) pre = tr_compose(pre, warp_tot[warp - 1]);
+      pre = tr_compose(pre, lanes_before);
+    }
+    unsigned n = n_in + ((n_in & 1u) ? pre.d1 : pre.d0);
+    unsigned nv[PS_E];
+    int cross = -1;
+    if (n < PS_TOP) {
+#pragma unroll
+      for (int j = 0; j < PS_E; ++j) {
+        const unsigned nn = n + ((n & 1u) ? el[j].d1 : el[j].d0);
+        if (cross < 0) {
+          if (nn >= PS_TOP) cross = j;
+          else n = nn;
+        }
+        nv[j] = n;
+      }
+      if (cross >= 0) atomicMin(&sh_cross, g0 + (unsigned)cross);
+    }
+    __syncthreads();
+    if (tid < PS_K) *cluster.map_shared_rank(&cta_min[rank], tid) = sh_cross;
+    cluster.sync();
+    unsigned c = PS_BK;  // addends committed in this binade; addend c (if < PS_BK) takes the real addition
+#pragma unroll
+    for (int r = 0; r < PS_K; ++r) c = umin(c, cta_min[r]);
+    if (c > 0u && (c - 1u) / (unsigned)PS_E == rank * (unsigned)PS_NT + (unsigned)tid) {
+      const int idx = (int)((c - 1u) % PS_E);
+      unsigned v = 0u;
+#pragma unroll
+      for (int j = 0; j < PS_E; ++j)
+        if (j == idx) v = nv[j];
+      for (int r = 0; r < PS_K; ++r) *cluster.map_shared_rank(&sh_n, r) = v;
+    }
+    if (c < PS_BK && c / (unsigned)PS_E == rank * (unsigned)PS_NT + (unsigned)tid) {
+      const int idx = (int)(c % PS_E);
+      float v = 0.0f;
+#pragma unroll
+      for (int j = 0; j < PS_E; ++j)
+        if (j == idx) v = a[j];
+      for (int r = 0; r < PS_K; ++r) *cluster.map_shared_rank(&sh_a, r) = v;
+    }
+    cluster.sync();
+    if (c > 0u) s = __uint_as_float(((unsigned)(e + 126) << 23) + sh_n);
+    pos += c;
+    if (c < PS_BK) {
+      s = fadd(s, sh_a);
+      pos += 1;
+    }
+    // the next round's first remote writes (cta_tot) come behind its own barriers; sh_n / sh_a / cta_min are
+    // rewritten only behind the next round's cluster barriers, which every thread reaches after these reads
+  }
+  cluster.sync();  // nobody leaves while a peer may still write into its shared memory
+  if (rank == 0 && tid == 0) reinterpret_cast<float*>(p.sums)[col] = s;
+}
+
 // gains[c] = sqrt(mean_x[c]) / sqrt(mean_y[c] + eps) with numpy's dtype chain: the mean divides in
 // float64 (np.mean's true_divide by an intp count) and stores the array dtype; eps is a weak
 // Python float, i.e. it is cast to the array dtype.  sums = [x columns..., y columns...].
@@ -520,8 +686,13 @@ int seq_sumsq_launch(const vnd_signal* a, const vnd_signal* b, void* sums, cudaS
     const char* e = getenv("VND_SEQSUM_SERIAL");  // testing: the scalar chain for every length
     return e && e[0] == '1';
   }();
+  static const bool cluster_ok = [] {
+    const char* e = getenv("VND_SEQSUM_CLUSTER");  // testing: 0 keeps the single-CTA scan
+    return !(e && e[0] == '0');
+  }();
   if (a->dtype == VND_F64) seq_sumsq_kernel<double><<<cols, 256, 0, st>>>(p);
   else if (serial_only || a->frames < 4096) seq_sumsq_kernel<float><<<cols, 256, 0, st>>>(p);
+  else if (cluster_ok && a->frames >= (long long)PS_HEAD + 2 * PS_B) seq_sumsq_cluster_kernel<<<cols * PS_K, PS_NT, 0, st>>>(p);
   else seq_sumsq_par_kernel<<<cols, PS_NT, 0, st>>>(p);
   return after_launch("seq_sumsq_kernel");
 }
