@@ -578,3 +578,17 @@ def test_sequential_sum_of_squares_is_numpy_order(kind, frames):
     # a strided view (every second column of a wider slab) reads the same values
     wide = torch.from_numpy(np.repeat(x, 2, axis=1)).cuda()
     assert same(_colsumsq(wide[:, ::2]), want)
+
+
+@pytest.mark.parametrize("kind", ["audio", "range", "ties"])
+def test_sequential_sum_of_squares_many_columns(kind):
+    """With many columns the scan runs on one CTA per column (the cluster of CTAs per column is for few columns,
+    where SMs would idle): same bits."""
+    import torch
+
+    frames = 100003
+    rng = np.random.default_rng(11 + len(kind))
+    x = np.concatenate([_seq_columns(rng, kind, frames) for _ in range(14)], axis=1)  # 42 columns
+    want = np.array([O.seq_sumsq_f32(x[:, c]) for c in range(x.shape[1])], dtype=np.float32)
+    got = _colsumsq(torch.from_numpy(x).cuda())
+    assert G.same_bits(got, want)

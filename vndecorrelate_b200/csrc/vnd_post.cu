@@ -686,13 +686,20 @@ int seq_sumsq_launch(const vnd_signal* a, const vnd_signal* b, void* sums, cudaS
     const char* e = getenv("VND_SEQSUM_SERIAL");  // testing: the scalar chain for every length
     return e && e[0] == '1';
   }();
+  DeviceInfo di;
+  {
+    const int rc = device_info(&di);
+    if (rc) return rc;
+  }
+  const int sm_count = di.sm_count;
   static const bool cluster_ok = [] {
     const char* e = getenv("VND_SEQSUM_CLUSTER");  // testing: 0 keeps the single-CTA scan
     return !(e && e[0] == '0');
   }();
   if (a->dtype == VND_F64) seq_sumsq_kernel<double><<<cols, 256, 0, st>>>(p);
   else if (serial_only || a->frames < 4096) seq_sumsq_kernel<float><<<cols, 256, 0, st>>>(p);
-  else if (cluster_ok && a->frames >= (long long)PS_HEAD + 2 * PS_B) seq_sumsq_cluster_kernel<<<cols * PS_K, PS_NT, 0, st>>>(p);
+  else if (cluster_ok && a->frames >= (long long)PS_HEAD + 2 * PS_B && cols * PS_K <= 2 * sm_count)  // few columns: latency matters, SMs are idle
+    seq_sumsq_cluster_kernel<<<cols * PS_K, PS_NT, 0, st>>>(p);
   else seq_sumsq_par_kernel<<<cols, PS_NT, 0, st>>>(p);
   return after_launch("seq_sumsq_kernel");
 }
