@@ -371,3 +371,35 @@ def test_pinned_output_pool_falls_back_without_a_device():
     if not has_gpu:
         assert R._POOL_BYTES[0] == before
     assert R.pinned_empty((0, 2), np.float32).shape == (0, 2)
+
+
+def test_kappa_family_program_equals_table_by_table_packing():
+    """taps.kappa_family_program (one vectorised pass for the candidates of optimize_velvet_noise) must produce the
+    very program candidate_program builds from one VelvetNoise per candidate, or decline (None)."""
+    from vndecorrelate_b200 import taps as T
+    from vndecorrelate_b200.decorrelation import VelvetNoise
+
+    rng = np.random.default_rng(0)
+    identical = declined = 0
+    for trial in range(48):
+        fs = int(rng.choice([44100, 48000, 96000]))
+        dur = float(rng.choice([0.004, 0.01, 0.03, 0.06]))
+        n_imp = int(rng.choice([5, 16, 30]))
+        env = [(0.85, 0.55, 0.35, 0.2), (1.0,), (0.9, -0.5), (0.5, 0.4, 0.3, 0.2, 0.1, 0.05)][trial % 4]
+        seed = int(rng.integers(0, 100))
+        kappas = rng.uniform(0, 1, 9)
+        kappas[0], kappas[1] = 0.0, 1.0
+        frames = int(rng.choice([100, 2000, 100000]))
+        cands = [VelvetNoise(sample_rate_hz=fs, duration_seconds=dur, num_impulses=n_imp, log_distribution_strength=float(k), normalizer=None,
+                             filtered_channels=(0,), mode="LR", seed=seed, segment_envelope=env) for k in kappas]
+        want = T.candidate_program([d.velvet_noise for d in cands], cands[0].segment_envelope, frames)
+        got = T.kappa_family_program(kappas, sample_rate_hz=fs, duration_seconds=dur, num_impulses=n_imp, envelope=cands[0].segment_envelope,
+                                     seed=seed, frames=frames)
+        if got is None:
+            declined += 1
+            continue
+        identical += 1
+        assert np.array_equal(got.words, want.words) and np.array_equal(got.offsets, want.offsets)
+        assert (got.channels, got.order, got.apply_gain, got.halo, got.max_channel_words) == (
+            want.channels, want.order, want.apply_gain, want.halo, want.max_channel_words)
+    assert identical >= 10 and declined >= 1  # both branches exercised

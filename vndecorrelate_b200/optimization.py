@@ -24,7 +24,7 @@ import numpy as np
 from . import _native as N
 from . import runtime as R
 from .decorrelation import Decorrelator, HaasEffect, VelvetNoise, _is_mode
-from .taps import IDENTITY_ENVELOPE, TapProgram, candidate_program
+from .taps import IDENTITY_ENVELOPE, TapProgram, candidate_program, kappa_family_program
 from .utils.dsp import EPSILON, LayoutMode
 
 __all__ = [
@@ -423,15 +423,25 @@ def optimize_velvet_noise(*, input_signal, sample_rate_hz: int, duration_seconds
                            log_distribution_strength=kappa, normalizer=None, filtered_channels=(0,), mode="LR", seed=seed)
 
     kappas = np.linspace(0.0, 1.0, grid_size)
-    scores = grid_scan(input_signal, [candidate(k) for k in kappas], **kw)
-    local_minima = get_local_minima(scores, grid_size)
     x = _as_stereo_f32(input_signal)
     clip = _device_clip(x)
+    envelope = candidate(0.0).segment_envelope
+
+    def family_program(ks):
+        """The candidates of the sweep differ only in the strength and share their random draws: their tap
+        programs are packed in one vectorised pass (taps.kappa_family_program), table by table only when
+        that shortcut does not apply."""
+        prog = kappa_family_program(ks, sample_rate_hz=sample_rate_hz, duration_seconds=duration_seconds, num_impulses=num_impulses,
+                                    envelope=envelope, seed=seed, frames=x.shape[0]) if seed is not None else None
+        return prog if prog is not None else _vn_family_program([candidate(k) for k in ks], x.shape[0])
 
     def batch(ks):
-        prog = _vn_family_program([candidate(k) for k in ks], x.shape[0])
-        p = vn_objective_partials(clip, prog)
+        p = vn_objective_partials(clip, family_program(ks))
         p = p.cpu().numpy() if R.is_torch_tensor(p) else p
         return list(vn_scores_from_partials(p, **kw)[0])
+
+    print("Starting Grid Scan")  # grid_scan's message (optimization.py:112)
+    scores = np.asarray(batch(kappas))
+    local_minima = get_local_minima(scores, grid_size)
 
     return optimize_local_minima_batched(local_minima, kappas, grid_size, batch)

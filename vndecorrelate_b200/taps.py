@@ -376,3 +376,52 @@ def candidate_program(tables: Sequence[TapTable], envelope: Sequence[float], fra
         np.ascontiguousarray(words, dtype=np.int32), offsets.astype(np.int32), len(progs), N.ORDER_SEGMENTED,
         progs[0].apply_gain if progs else 0, max((p.halo for p in progs), default=0), int(sizes.max()) if len(sizes) else 0,
     )
+
+
+def kappa_family_program(kappas, *, sample_rate_hz: int, duration_seconds: float, num_impulses: int, envelope: Sequence[float], seed,
+                         frames: int) -> TapProgram | None:
+    """``candidate_program`` for the family ``optimize_velvet_noise`` sweeps (optimization.py:260-272): stereo
+    ``VelvetNoise`` candidates with ``filtered_channels=(0,)`` that differ only in ``log_distribution_strength``.
+
+    With one seed every candidate draws the SAME uniforms (decorrelation.py:488, :510-521), so the signs, the
+    decay segments and with them the order of the taps in a program are common to the family; only the interval
+    grid (``w``, ``starts``) depends on the strength.  The grid is still computed per candidate by the functions
+    the single-table path uses (same array shapes, hence the same numpy code paths and bits); positions, rounding
+    and packing are done for all candidates at once.  Returns None when the shortcut does not apply (a tap at or
+    beyond ``frames``, an empty decay segment, no impulses): the caller then packs table by table."""
+    kappas = [float(k) for k in kappas]
+    K = len(kappas)
+    S = len(envelope)
+    if K == 0 or num_impulses <= 0 or S == 0:
+        return None
+    identity = tuple(envelope) == IDENTITY_ENVELOPE
+    fir_length = int(round(sample_rate_hz * duration_seconds))
+    sign_u, offs_u = _draw(seed, num_impulses, 1)  # one filtered channel: channel 0
+    jitter = sample_rate_hz / (num_impulses / duration_seconds)
+    grids = [_interval_grid(k, num_impulses, fir_length) for k in kappas]
+    w = np.stack([g[0] for g in grids])          # (K, N + 1)
+    starts = np.stack([g[1] for g in grids])     # (K, N + 1)
+    pos = np.round(offs_u[:, 0][None, :] * np.fmax(0.0, w * jitter - 1) + starts).astype(np.int32)[:, :num_impulses]
+    positive = np.round(sign_u[:, 0]) == 1.0     # (N,)
+    segment = _segment_of_impulse(num_impulses, S)
+    if int(pos.max()) >= frames or int(pos.min()) < 0:
+        return None
+    key = segment * 2 + positive                  # iteration order: segment, then negative before positive
+    order = np.argsort(key, kind="stable")
+    counts = np.zeros(2 * S, dtype=np.int64)
+    np.add.at(counts, key, 1)
+    counts = counts.reshape(S, 2)
+    if (counts.sum(axis=1) == 0).any():
+        return None
+    gains = np.ones(S, dtype=np.float32) if identity else np.array([float(envelope[s]) for s in range(S)], dtype=np.float64).astype(np.float32)
+    head = np.empty(1 + 3 * S, dtype=np.int32)
+    head[0] = S
+    head[1::3] = counts[:, 0]
+    head[2::3] = counts[:, 1]
+    head[3::3] = gains.view(np.int32)
+    block = 1 + 3 * S + num_impulses
+    words = np.empty((K, block), dtype=np.int32)
+    words[:, : 1 + 3 * S] = head
+    words[:, 1 + 3 * S:] = pos[:, order]
+    offsets = (np.arange(K + 1, dtype=np.int64) * block).astype(np.int32)
+    return TapProgram(np.ascontiguousarray(words.reshape(-1)), offsets, K, N.ORDER_SEGMENTED, 0 if identity else 1, int(pos.max()) + 1, block)
