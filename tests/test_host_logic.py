@@ -403,3 +403,50 @@ def test_kappa_family_program_equals_table_by_table_packing():
         assert (got.channels, got.order, got.apply_gain, got.halo, got.max_channel_words) == (
             want.channels, want.order, want.apply_gain, want.halo, want.max_channel_words)
     assert identical >= 10 and declined >= 1  # both branches exercised
+
+
+def test_bounded_brent_coroutine_is_scipys_minimiser():
+    """optimization._bounded_brent (the lock-step refinement) against scipy.optimize.minimize_scalar(method="bounded"),
+    the routine the reference calls (optimization.py:144-149): same abscissae in the same order, same minimum, same
+    value and dtype, same evaluation count - for float32-valued objectives (what the velvet-noise score is),
+    float64-valued ones (Haas), plateaus with ties, and Python floats."""
+    from scipy.optimize import minimize_scalar
+
+    from vndecorrelate_b200.optimization import lockstep_minimize
+
+    def make(kind, seed):
+        c = np.random.default_rng(seed).uniform(0, 1, 4)
+        if kind == 0:
+            return lambda x: np.float32((x - c[0]) ** 2 + 0.01 * np.sin(50 * x * c[1]))
+        if kind == 1:
+            return lambda x: np.float32(np.abs(x - c[0]) + 0.3 * np.cos(37 * x))
+        if kind == 2:
+            return lambda x: float(np.sin(20 * x * c[2]) + x * c[3])
+        if kind == 3:
+            return lambda x: np.float32(np.round(np.sin(30 * x) * 8) / 8)
+        return lambda x: np.float64(np.cos(11 * x * c[0]) * np.exp(-x) + c[1] * x * x)
+
+    rng = np.random.default_rng(1)
+    for kind in range(5):
+        for seed in range(25):
+            f = make(kind, seed)
+            lo = np.float64(rng.uniform(0, 0.5))
+            hi = lo + np.float64(rng.uniform(1e-3, 0.5))
+            seen_ref, seen = [], []
+            want = minimize_scalar(fun=lambda x: (seen_ref.append(float(x)), f(x))[1], bounds=(lo, hi), method="bounded", options={"xatol": 1e-4})
+            got = lockstep_minimize([(lo, hi)], lambda xs: [(seen.append(x), f(x))[1] for x in xs], xatol=1e-4)[0]
+            assert seen == seen_ref
+            assert got.x == want.x and type(got.x) is type(want.x)
+            assert got.fun == want.fun and type(got.fun) is type(want.fun)
+            assert (got.nfev, got.status, got.success) == (want.nfev, want.status, want.success)
+
+
+def test_lockstep_minimize_batches_all_minimisers():
+    from vndecorrelate_b200.optimization import lockstep_minimize
+
+    calls = []
+    bounds = [(i / 64, (i + 2) / 64) for i in range(0, 62, 3)]
+    res = lockstep_minimize(bounds, lambda xs: (calls.append(len(xs)), [np.float32((x - 0.4) ** 2) for x in xs])[1])
+    assert len(res) == len(bounds) and all(r is not None and r.success for r in res)
+    assert calls[0] == len(bounds) and calls == sorted(calls, reverse=True)  # everybody in the first round, finished ones drop out
+    assert lockstep_minimize([], lambda xs: []) == []

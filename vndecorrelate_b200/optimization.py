@@ -289,78 +289,126 @@ def optimize_local_minima(local_minima: list[int], scalars, grid_size: int, scal
     return best_scalar
 
 
+def _bounded_brent(x1, x2, xatol: float, maxiter: int = 500):
+    """Brent's bounded scalar minimiser as a coroutine: yields the next abscissa, is sent the function value, and
+    returns an ``OptimizeResult`` when it has converged.
+
+    This is the algorithm behind ``scipy.optimize.minimize_scalar(method="bounded")`` - the reference's refinement
+    step (optimization.py:144-149) - restated statement for statement after ``_minimize_scalar_bounded`` of the
+    pinned scipy (1.16 in the reference's lock file, 1.18 here; the routine is Forsythe, Malcolm and Moler's
+    ``fmin``), with the same expressions on the same operand types, so that numpy's promotion rules give every
+    intermediate the dtype it has there (the objective returns ``np.float32``) and every comparison comes out the
+    same.  ``tests/test_host_logic.py`` pins it against scipy itself (abscissae, values, evaluation counts).
+    Written as a coroutine so that hundreds of minimisers advance in lock-step without a thread each."""
+    from math import sqrt
+
+    from scipy.optimize import OptimizeResult
+
+    if not (np.isfinite(x1) and np.isfinite(x2)):
+        raise ValueError("Optimization bounds must be finite scalars.")
+    if x1 > x2:
+        raise ValueError("The lower bound exceeds the upper bound.")
+    flag = 0
+    sqrt_eps = sqrt(2.2e-16)
+    golden_mean = 0.5 * (3.0 - sqrt(5.0))
+    a, b = x1, x2
+    fulc = a + golden_mean * (b - a)
+    nfc, xf = fulc, fulc
+    rat = e = 0.0
+    x = xf
+    fx = yield x
+    num = 1
+    fu = np.inf
+    ffulc = fnfc = fx
+    xm = 0.5 * (a + b)
+    tol1 = sqrt_eps * np.abs(xf) + xatol / 3.0
+    tol2 = 2.0 * tol1
+    while np.abs(xf - xm) > (tol2 - 0.5 * (b - a)):
+        golden = 1
+        if np.abs(e) > tol1:  # try a parabolic step
+            golden = 0
+            r = (xf - nfc) * (fx - ffulc)
+            q = (xf - fulc) * (fx - fnfc)
+            p = (xf - fulc) * q - (xf - nfc) * r
+            q = 2.0 * (q - r)
+            if q > 0.0:
+                p = -p
+            q = np.abs(q)
+            r = e
+            e = rat
+            if (np.abs(p) < np.abs(0.5 * q * r)) and (p > q * (a - xf)) and (p < q * (b - xf)):
+                rat = (p + 0.0) / q
+                x = xf + rat
+                if ((x - a) < tol2) or ((b - x) < tol2):
+                    si = np.sign(xm - xf) + ((xm - xf) == 0)
+                    rat = tol1 * si
+            else:
+                golden = 1
+        if golden:  # golden-section step
+            if xf >= xm:
+                e = a - xf
+            else:
+                e = b - xf
+            rat = golden_mean * e
+        si = np.sign(rat) + (rat == 0)
+        x = xf + si * np.maximum(np.abs(rat), tol1)
+        fu = yield x
+        num += 1
+        if fu <= fx:
+            if x >= xf:
+                a = xf
+            else:
+                b = xf
+            fulc, ffulc = nfc, fnfc
+            nfc, fnfc = xf, fx
+            xf, fx = x, fu
+        else:
+            if x < xf:
+                a = x
+            else:
+                b = x
+            if (fu <= fnfc) or (nfc == xf):
+                fulc, ffulc = nfc, fnfc
+                nfc, fnfc = x, fu
+            elif (fu <= ffulc) or (fulc == xf) or (fulc == nfc):
+                fulc, ffulc = x, fu
+        xm = 0.5 * (a + b)
+        tol1 = sqrt_eps * np.abs(xf) + xatol / 3.0
+        tol2 = 2.0 * tol1
+        if num >= maxiter:
+            flag = 1
+            break
+    if np.isnan(xf) or np.isnan(fx) or np.isnan(fu):
+        flag = 2
+    return OptimizeResult(fun=np.asarray(fx)[()], status=flag, success=(flag == 0), x=xf, nfev=num, nit=num)  # numpy scalar, as minimize_scalar returns it
+
+
 def lockstep_minimize(bounds: Sequence[tuple[float, float]], batch_objective: Callable[[list[float]], Sequence[Any]], *, xatol: float = 1e-4):
-    """Run scipy's bounded Brent minimiser on many intervals at once, in lock-step.
+    """Run the bounded Brent minimiser on many intervals at once, in lock-step.
 
-    Every interval gets its own ``scipy.optimize.minimize_scalar(method="bounded")`` — the reference's
-    refinement step (optimization.py:144-149), unchanged, so every comparison it makes is the one the
-    reference makes — running in its own thread.  Whenever all live minimisers are waiting for a
-    function value, the pending abscissae are evaluated with ONE call of ``batch_objective`` (one
-    kernel launch over all of them) and handed back.  Returns the ``OptimizeResult`` list in input
-    order.  The sequence of abscissae each minimiser sees depends only on its own function values, so
-    the results equal those of the one-at-a-time loop whenever ``batch_objective`` returns the values
-    the scalar objective would."""
-    import threading
-
-    from scipy.optimize import minimize_scalar
-
+    Every interval gets its own minimiser (``_bounded_brent``: the reference's refinement step,
+    optimization.py:144-149, comparison for comparison).  In every round the pending abscissae of all live
+    minimisers are evaluated with ONE call of ``batch_objective`` (one kernel launch over all of them) and handed
+    back.  Returns the ``OptimizeResult`` list in input order.  The sequence of abscissae each minimiser sees
+    depends only on its own function values, so the results equal those of the one-at-a-time loop whenever
+    ``batch_objective`` returns the values the scalar objective would."""
     n = len(bounds)
-    if n == 0:
-        return []
-    cond = threading.Condition()
-    pending: dict[int, float] = {}
-    answers: dict[int, Any] = {}
     results: list[Any] = [None] * n
-    errors: list[BaseException] = []
-    alive = n
-
-    def worker(i: int, lo: float, hi: float) -> None:
-        nonlocal alive
-
-        def fn(x):
-            with cond:
-                pending[i] = float(x)
-                cond.notify_all()
-                while i not in answers and not errors:
-                    cond.wait()
-                if errors:
-                    raise RuntimeError("lock-step evaluation failed") from errors[0]
-                return answers.pop(i)
-
-        try:
-            results[i] = minimize_scalar(fun=fn, bounds=(lo, hi), method="bounded", options={"xatol": xatol})
-        except BaseException as exc:  # surfaced by the coordinator
-            with cond:
-                errors.append(exc)
-        finally:
-            with cond:
-                alive -= 1
-                cond.notify_all()
-
-    threads = [threading.Thread(target=worker, args=(i, lo, hi), daemon=True) for i, (lo, hi) in enumerate(bounds)]
-    for t in threads:
-        t.start()
-    with cond:
-        while alive > 0 and not errors:
-            while len(pending) < alive and alive > 0 and not errors:
-                cond.wait()
-            if errors or alive == 0:
-                break
-            ids = sorted(pending)
-            xs = [pending.pop(i) for i in ids]
+    live: dict[int, Any] = {}
+    pending: dict[int, Any] = {}
+    for i, (lo, hi) in enumerate(bounds):
+        gen = _bounded_brent(lo, hi, xatol)
+        live[i] = gen
+        pending[i] = next(gen)  # the first abscissa (a minimiser always evaluates at least once)
+    while live:
+        ids = sorted(live)
+        vals = batch_objective([float(pending[i]) for i in ids])
+        for i, v in zip(ids, vals):
             try:
-                vals = batch_objective(xs)
-            except BaseException as exc:
-                errors.append(exc)
-                cond.notify_all()
-                break
-            for i, v in zip(ids, vals):
-                answers[i] = v
-            cond.notify_all()
-    for t in threads:
-        t.join()
-    if errors:
-        raise errors[0]
+                pending[i] = live[i].send(v)
+            except StopIteration as done:
+                results[i] = done.value
+                del live[i], pending[i]
     return results
 
 
