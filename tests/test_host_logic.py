@@ -450,3 +450,33 @@ def test_lockstep_minimize_batches_all_minimisers():
     assert len(res) == len(bounds) and all(r is not None and r.success for r in res)
     assert calls[0] == len(bounds) and calls == sorted(calls, reverse=True)  # everybody in the first round, finished ones drop out
     assert lockstep_minimize([], lambda xs: []) == []
+
+
+def test_vectorised_scores_equal_the_one_row_chain_bit_for_bit():
+    """optimization._vn_scores_rows (all (clip, candidate) pairs at once) against _vn_score (one pair, the reference's
+    scalar dtype chain): identical float32 bits, including rows with and without a frame on the
+    negative half plane and rows that exceed the angle limit."""
+    import vndecorrelate_b200.optimization as OPT
+    from vndecorrelate_b200 import _native as N
+
+    kw = dict(angle_limit=np.pi / 4, lambda_mean=5.0, lambda_skew=2.0, lambda_correlation=15.0, lambda_penalty=1e3)
+    rng = np.random.default_rng(3)
+    n = 6000
+    p = np.zeros((n, N.OBJ_SLOTS))
+    sr = rng.uniform(1e2, 1e6, n)
+    p[:, 0] = sr
+    p[:, 1] = sr * rng.normal(0, 0.3, n)
+    p[:, 2] = sr * rng.uniform(0, 0.8, n)
+    p[:, 3] = sr * rng.normal(0, 0.2, n)
+    p[:, 5] = rng.uniform(1, 1e5, n)
+    p[:, 4] = p[:, 5] * rng.uniform(-1, 1, n)
+    p[:, 6] = np.float32(rng.uniform(0, 2, n))
+    p[:, 7] = np.float32(rng.uniform(1e-6, 1, n))
+    p[:, 8] = np.float32(rng.uniform(0, 2, n))
+    p[:, 9] = np.float32(rng.uniform(1e-6, 1, n))
+    untouched = rng.random(n) < 0.2
+    p[untouched, 8], p[untouched, 9] = 0.0, 1.0
+    want = np.array([OPT._vn_score(r, **kw) for r in p], dtype=np.float32)
+    got = OPT.vn_scores_from_partials(p.reshape(60, 100, -1), **kw)
+    assert got.dtype == np.float32 and got.shape == (60, 100)
+    assert np.array_equal(got.reshape(-1).view(np.uint32), want.view(np.uint32))

@@ -172,10 +172,39 @@ def _haas_score(p: np.ndarray, angle_limit, lambda_mean, lambda_skew, lambda_cor
     return np.float64(-objective)
 
 
+def _vn_scores_rows(flat: np.ndarray, angle_limit, lambda_mean, lambda_skew, lambda_correlation, lambda_penalty) -> np.ndarray:
+    """``_vn_score`` for many rows at once: the same operations in the same dtypes, element by element (IEEE basic
+    operations give the same bits in an array as on scalars); the library calls - every ``**`` and ``arctan2`` on
+    float64 scalars - stay scalar calls, so that no vector math library can round them
+    differently from the one-row chain.  ``tests/test_host_logic.py`` asserts bit equality with ``_vn_score``."""
+    p = np.asarray(flat, dtype=np.float64)
+    eps32 = np.float32(EPSILON)
+    denom = (p[:, 0].astype(np.float32) + eps32).astype(np.float64)          # float32 sum, widened for the divisions
+    spread = (p[:, 2] / denom).astype(np.float32).astype(np.float64)         # float(np.float32(...)) per row
+    cen = (p[:, 1] / denom).astype(np.float32).astype(np.float64)
+    m3 = (p[:, 3] / denom).astype(np.float32).astype(np.float64)
+    skew = m3 / np.array([m ** 1.5 for m in np.maximum(spread, EPSILON).tolist()], dtype=np.float64)
+    nl = (np.sqrt(p[:, 5]).astype(np.float32) + eps32).astype(np.float64)
+    corr = (p[:, 4] / (nl * nl)).astype(np.float32)
+    max_theta = np.array([_max_abs_theta_f32(row) for row in p], dtype=np.float32)
+    exceed = np.maximum(0.0, (max_theta - np.float32(angle_limit)).astype(np.float64))
+    # every power stays the scalar call of the one-row chain (float ** 2 is C pow, np.float32 ** 2 is powf: neither is
+    # guaranteed to round like x * x, which is what an array power would compute)
+    sq = lambda v: np.array([t ** 2 for t in v.tolist()], dtype=np.float64)  # noqa: E731  (Python floats)
+    partial = spread - lambda_mean * sq(cen) - lambda_skew * sq(skew)       # Python-float arithmetic in the one-row chain
+    corr2 = np.array([c ** 2 for c in corr], dtype=np.float32)               # np.float32 scalars
+    lr_pen = (np.float32(lambda_correlation) * corr2).astype(np.float32)    # weak Python scalar times float32
+    objective = partial.astype(np.float32) - lr_pen                          # float minus np.float32 -> np.float32
+    objective = objective - (lambda_penalty * sq(exceed)).astype(np.float32)
+    return -objective
+
+
 def vn_scores_from_partials(partials, **kw) -> np.ndarray:
     p = partials.cpu().numpy() if R.is_torch_tensor(partials) else np.asarray(partials)
     flat = p.reshape(-1, N.OBJ_SLOTS)
-    return np.array([_vn_score(row, **kw) for row in flat], dtype=np.float32).reshape(p.shape[:-1])
+    if len(flat) == 0:
+        return np.zeros(p.shape[:-1], dtype=np.float32)
+    return _vn_scores_rows(flat, **kw).astype(np.float32).reshape(p.shape[:-1])
 
 
 def haas_scores_from_partials(partials, **kw) -> np.ndarray:
