@@ -592,3 +592,17 @@ def test_sequential_sum_of_squares_many_columns(kind):
     want = np.array([O.seq_sumsq_f32(x[:, c]) for c in range(x.shape[1])], dtype=np.float32)
     got = _colsumsq(torch.from_numpy(x).cuda())
     assert G.same_bits(got, want)
+
+
+def test_sequential_sum_of_squares_full_length():
+    """BASELINE config 3's channel length (10 min @ 48 kHz = 28.8 M frames): about 3 500 scan rounds per column on
+    the cluster path, the sum crossing 20 binades; still numpy's left-to-right float32 sum bit for bit."""
+    import torch
+
+    frames = 28_800_000
+    rng = np.random.default_rng(2024)
+    x = (rng.standard_normal((frames, 2)) * 0.1).astype(np.float32)
+    x[:, 1] *= np.float32(30.0)
+    want = np.array([O.seq_sumsq_f32(x[:, c]) for c in range(2)], dtype=np.float32)
+    got = _colsumsq(torch.from_numpy(x).cuda())
+    assert G.same_bits(got, want), (got, want)
