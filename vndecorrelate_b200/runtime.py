@@ -142,7 +142,7 @@ class _PinnedBlock:
         _pinned_pool_release(self.ptr, self.nbytes)
 
 
-_POOL_LOCK = threading.Lock()
+_POOL_LOCK = threading.RLock()  # re-entrant: a garbage collection inside the locked region may release another block
 _POOL_FREE: dict[int, list[int]] = {}   # block size -> free pointers
 _POOL_BYTES = [0]                       # page-locked bytes this pool has allocated
 _POOL_CAP = int(os.environ.get("VND_PINNED_POOL_MB", "512")) << 20
