@@ -480,3 +480,42 @@ def test_vectorised_scores_equal_the_one_row_chain_bit_for_bit():
     got = OPT.vn_scores_from_partials(p.reshape(60, 100, -1), **kw)
     assert got.dtype == np.float32 and got.shape == (60, 100)
     assert np.array_equal(got.reshape(-1).view(np.uint32), want.view(np.uint32))
+
+
+def test_pinned_output_pool_recycles_blocks(monkeypatch):
+    """The pool's life-cycle with a stand-in allocator (malloc instead of cudaHostAlloc): a block stays out while
+    any view of the array lives, comes back when the last one dies, and is handed out again."""
+    import ctypes as C
+    import gc
+
+    from vndecorrelate_b200 import _native as N
+    from vndecorrelate_b200 import runtime as R
+
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.malloc.argtypes = [C.c_size_t]
+
+    class FakeLib:
+        def vnd_host_alloc(self, nbytes, out):
+            C.cast(out, C.POINTER(C.c_void_p))[0] = libc.malloc(nbytes)
+            return 0
+
+    monkeypatch.setattr(N, "lib", lambda: FakeLib())
+    monkeypatch.setattr(R, "_POOL_FREE", {})
+    monkeypatch.setattr(R, "_POOL_BYTES", [0])
+    a = R.pinned_empty((1000, 2), np.float32)
+    assert a.flags.writeable and not a.flags.owndata and R._POOL_BYTES[0] == 1 << 16
+    a[:] = 1.5
+    ptr = a.ctypes.data
+    view = a[10:20]
+    del a
+    gc.collect()
+    assert sum(len(v) for v in R._POOL_FREE.values()) == 0 and float(view[0, 0]) == 1.5  # the view keeps the block
+    del view
+    gc.collect()
+    assert sum(len(v) for v in R._POOL_FREE.values()) == 1
+    b = R.pinned_empty((500, 4), np.float32)  # same block size: recycled, no new allocation
+    assert b.ctypes.data == ptr and R._POOL_BYTES[0] == 1 << 16
+    monkeypatch.setattr(R, "_POOL_CAP", 1 << 16)
+    c = R.pinned_empty((1 << 15,), np.float32)  # 128 KB more would exceed the cap: ordinary memory
+    assert c.flags.owndata
