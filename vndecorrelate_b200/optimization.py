@@ -143,6 +143,18 @@ def _max_abs_theta_f32(p: np.ndarray) -> np.float32:
     return np.float32(best)
 
 
+def _max_abs_theta_rows(p: np.ndarray) -> np.ndarray:
+    """``_max_abs_theta_f32`` for many rows (the array ``arctan2`` runs the same numpy loop as the scalar call; the
+    CPU tests compare the two bit for bit)."""
+    d_pos, s_pos, d_neg, s_neg = p[:, 6], p[:, 7], p[:, 8], p[:, 9]
+    best = np.arctan2(d_pos, s_pos).astype(np.float32)
+    seen = (d_neg > 0.0) | (s_neg != 1.0)  # a frame with s < 0 was seen (the tracker starts at 0 / 1)
+    t = np.arctan2(d_neg, -s_neg).astype(np.float32)
+    t = np.where(t > _F32_HALF_PI, (t - _F32_PI).astype(np.float32), t)
+    cand = np.abs(t)
+    return np.where(seen & (cand > best), cand, best).astype(np.float32)  # Python's max(best, cand): cand only if greater
+
+
 def _vn_score(p: np.ndarray, angle_limit, lambda_mean, lambda_skew, lambda_correlation, lambda_penalty) -> np.float32:
     denom = np.float32(np.float32(p[0]) + np.float32(EPSILON))  # radii.sum() + EPSILON, float32 (utils/dsp.py:418)
     spread = float(np.float32(p[2] / np.float64(denom)))  # optimization.py:19-21
@@ -174,8 +186,8 @@ def _haas_score(p: np.ndarray, angle_limit, lambda_mean, lambda_skew, lambda_cor
 
 def _vn_scores_rows(flat: np.ndarray, angle_limit, lambda_mean, lambda_skew, lambda_correlation, lambda_penalty) -> np.ndarray:
     """``_vn_score`` for many rows at once: the same operations in the same dtypes, element by element (IEEE basic
-    operations give the same bits in an array as on scalars); the library calls - every ``**`` and ``arctan2`` on
-    float64 scalars - stay scalar calls, so that no vector math library can round them
+    operations give the same bits in an array as on scalars); every ``**`` stays the scalar call it is in the one-row
+    chain, so that no vector math library can round them
     differently from the one-row chain.  ``tests/test_host_logic.py`` asserts bit equality with ``_vn_score``."""
     p = np.asarray(flat, dtype=np.float64)
     eps32 = np.float32(EPSILON)
@@ -186,7 +198,7 @@ def _vn_scores_rows(flat: np.ndarray, angle_limit, lambda_mean, lambda_skew, lam
     skew = m3 / np.array([m ** 1.5 for m in np.maximum(spread, EPSILON).tolist()], dtype=np.float64)
     nl = (np.sqrt(p[:, 5]).astype(np.float32) + eps32).astype(np.float64)
     corr = (p[:, 4] / (nl * nl)).astype(np.float32)
-    max_theta = np.array([_max_abs_theta_f32(row) for row in p], dtype=np.float32)
+    max_theta = _max_abs_theta_rows(p)
     exceed = np.maximum(0.0, (max_theta - np.float32(angle_limit)).astype(np.float64))
     # every power stays the scalar call of the one-row chain (float ** 2 is C pow, np.float32 ** 2 is powf: neither is
     # guaranteed to round like x * x, which is what an array power would compute)
