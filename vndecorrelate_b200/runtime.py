@@ -146,7 +146,7 @@ _POOL_LOCK = threading.RLock()  # re-entrant: a garbage collection inside the lo
 _POOL_FREE: dict[int, list[int]] = {}   # block size -> free pointers
 _POOL_BYTES = [0]                       # page-locked bytes this pool has allocated
 _POOL_CAP = int(os.environ.get("VND_PINNED_POOL_MB", "512")) << 20
-_POOL_MAX_BLOCK = 128 << 20
+_POOL_MAX_BLOCK = 32 << 20           # larger results take ordinary memory: pinning them costs more than it saves on a first call
 
 
 def _pinned_pool_release(ptr: int, nbytes: int) -> None:
