@@ -104,3 +104,73 @@ def test_sweep_sharded_world2_gloo(tmp_path, by):
         assert np.array_equal(got, want)  # every rank holds the full matrix
     argmins, minima = S.select_from_scores(want)
     assert len(argmins) == 3 and all(0 <= a < 6 for a in argmins) and all(len(m) >= 1 for m in minima)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# optimize_velvet_noise_batch (BASELINE config 5): clips sharded, one all-gather of the score matrix, lock-step
+# refinement per rank.  On CPU the clip bank is replaced by one that scores with the oracle; partition, collective,
+# minima selection and the Brent bookkeeping are the code the NCCL path runs.
+# --------------------------------------------------------------------------------------------------------------
+_FS, _DUR, _NIMP, _GRID, _FRAMES = 48000, 0.03, 30, 24, 4000
+
+
+class _OracleBank:
+    def __init__(self, clips, family, kw):
+        self.clips = [np.ascontiguousarray(np.asarray(c)) for c in clips]
+        self.n, self.frames, self.device = len(self.clips), self.clips[0].shape[0], None
+        self.evaluations = self.launches = 0
+
+    def scores(self, requests):
+        out = []
+        for clip, ks in zip(self.clips, requests):
+            self.evaluations += len(ks)
+            out.append(np.asarray(O.vn_grid_scores(clip, list(ks), sample_rate_hz=_FS, duration_seconds=_DUR, num_impulses=_NIMP, seed=1),
+                                  dtype=np.float32) if len(ks) else np.zeros(0, np.float32))
+        return out
+
+
+def _batch_clips():
+    return [O.coloured_clip(i, _FRAMES) for i in range(5)]
+
+
+def _batch_worker(rank, world, port, result_dir):
+    import torch.distributed as dist
+
+    from vndecorrelate_b200 import optimization as OPT
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ks, info = OPT.optimize_velvet_noise_batch(input_signals=_batch_clips(), sample_rate_hz=_FS, duration_seconds=_DUR, num_impulses=_NIMP,
+                                                   seed=1, grid_size=_GRID, details=True, _bank_factory=_OracleBank)
+        np.save(os.path.join(result_dir, f"kappa_{rank}.npy"), ks)
+        np.save(os.path.join(result_dir, f"scores_{rank}.npy"), info["scores"])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_optimize_velvet_noise_batch_world2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+
+    from vndecorrelate_b200 import optimization as OPT
+
+    world = 2
+    mp.spawn(_batch_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    clips = _batch_clips()
+    # single process, same code
+    one, info = OPT.optimize_velvet_noise_batch(input_signals=clips, sample_rate_hz=_FS, duration_seconds=_DUR, num_impulses=_NIMP, seed=1,
+                                                grid_size=_GRID, details=True, _bank_factory=_OracleBank)
+    # the reference's procedure, clip by clip, one scipy minimiser at a time (oracle/vnd_oracle.py::refine)
+    kappas = np.linspace(0.0, 1.0, _GRID)
+    want = []
+    for c in clips:
+        row = np.asarray(O.vn_grid_scores(c, kappas, sample_rate_hz=_FS, duration_seconds=_DUR, num_impulses=_NIMP, seed=1), dtype=np.float32)
+        minima = OPT.get_local_minima(row, _GRID)
+        fn = lambda k, c=c: O.vn_grid_scores(c, [k], sample_rate_hz=_FS, duration_seconds=_DUR, num_impulses=_NIMP, seed=1)[0]  # noqa: E731
+        want.append(O.refine(minima, kappas, fn))
+    want = np.asarray(want, dtype=np.float64)
+    assert one.dtype == np.float64 and np.array_equal(one, want)
+    for r in range(world):
+        assert np.array_equal(np.load(os.path.join(str(tmp_path), f"kappa_{r}.npy")), want)          # every rank: all clips, same bits
+        assert np.array_equal(np.load(os.path.join(str(tmp_path), f"scores_{r}.npy")), info["scores"])  # and the full score matrix

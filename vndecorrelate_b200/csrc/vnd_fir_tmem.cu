@@ -55,6 +55,10 @@
 #define VND_TM_RUN_MIN 48   // fewest (a run pays a prologue and a pipeline fill of about two tiles)
 #endif
 
+#ifndef VND_TM_DEFAULT_SHAPE
+#define VND_TM_DEFAULT_SHAPE 0  // TmShape used unless VND_TM_SHAPE says otherwise (fir_tmem_launch)
+#endif
+
 #ifdef VND_TM_TRACE
 // Debug builds only: clock64() of a few events per warp and tile of CTA 0 (tools/trace_tmem.py).
 __device__ unsigned long long g_tm_trace[16][64][8];
@@ -76,26 +80,45 @@ namespace vnd {
 namespace {
 
 constexpr int kRows = 128;             // TMEM lanes = rows of a tile
-constexpr int kR = 96;                 // outputs per row
-constexpr int kG = 3;                  // compute warps per lane quarter
-constexpr int kRG = kR / kG;           // outputs per thread
-constexpr int kNP = kRG / 2;           // register pairs per thread
-constexpr int kCW = 4 * kG;            // compute warps (warp w: lane quarter w & 3, group w >> 2)
-constexpr int kNW = kCW + 4;           // plus one data-movement warp per quarter
-constexpr int kNT = kNW * 32;
-constexpr int kTile = kRows * kR;      // 12288 outputs
-constexpr int kPitch = kR + 4;         // row pitch in shared memory (words); 25 chunks: odd
 constexpr int kCols = 512;             // TMEM columns
 constexpr int kUnits = kCols / 32;     // 32-column units of a TMEM row
-constexpr int kNearMax = kCols - kR;   // largest tap offset served from TMEM
-constexpr int kNBuf = 3;               // tile buffers in shared memory
-constexpr int kRegsCompute = 144, kRegsHelper = 80;  // 12*32*144 + 4*32*80 == 65536
 constexpr int kBarBytes = 256;
-static_assert(kRG == 32, "a thread owns 32 outputs (one 32-column tcgen05.ld)");
-static_assert(kCW * 32 * kRegsCompute + 4 * 32 * kRegsHelper <= 65536, "register file");
 
-// mbarrier slots (uint64 each)
-enum { B_IN_FULL = 0, B_IN_FREE = 3, B_ST_FULL = 6, B_ST_FREE = 10, B_TM_FULL = 14, B_TM_FREE = 18, B_COUNT = 22 };
+// Shape of the kernel: G compute warps per lane quarter, each thread owning RG consecutive outputs of its
+// row (a row is R = G * RG outputs), NBUF tile buffers in shared memory, RC / RH registers per compute /
+// data-movement thread (setmaxnreg; 32 * (4 G RC + 4 RH) must not exceed what the launch allocates).
+//   <3, 32, 3, 144, 80>  round 1: 12 compute warps x 32 outputs, rows of 96, reach 416
+//   <2, 48, 3, 200, 104> 8 compute warps x 48 outputs, rows of 96: two warps per scheduler is where the
+//                        tensor-memory read path is efficient (tools/microbench/tmem_lat.cu: 8 warps 415 B/clk/SM,
+//                        12 warps 279), and every per-tap overhead is spread over 48 outputs instead of 32
+//   <2, 64, 2, 200, 104> 8 compute warps x 64 outputs, rows of 128: TMEM refill 4 instead of 5.33 words per output,
+//                        reach 384; two tile buffers (tile + halo is 74 KB)
+template <int G, int RG, int NBUF, int RC, int RH, bool PIPE = false>
+struct TmShape {
+  static constexpr bool kPipe = PIPE;          // tensor-memory taps software-pipelined over two operand buffers
+  static constexpr int kG = G;                 // compute warps per lane quarter
+  static constexpr int kRG = RG;               // outputs per thread
+  static constexpr int kR = G * RG;            // outputs per row
+  static constexpr int kCW = 4 * G;            // compute warps (warp w: lane quarter w & 3, group w >> 2)
+  static constexpr int kNW = kCW + 4;          // plus one data-movement warp per quarter
+  static constexpr int kNT = kNW * 32;
+  static constexpr int kTile = kRows * kR;
+  static constexpr int kPitch = kR + 4;        // row pitch in shared memory (words); an odd number of 16-byte chunks
+  static constexpr int kUnitsPerBlock = kR / 32;
+  static constexpr int kNBuf = NBUF;
+  static constexpr int kRegsCompute = RC, kRegsHelper = RH;
+  static constexpr int kLaunchRegs = (65536 / kNT) / 8 * 8;
+  // mbarrier slots (uint64 each)
+  static constexpr int B_IN_FULL = 0, B_IN_FREE = NBUF, B_ST_FULL = 2 * NBUF, B_ST_FREE = 2 * NBUF + 4, B_TM_FULL = 2 * NBUF + 8,
+                       B_TM_FREE = 2 * NBUF + 12, B_COUNT = 2 * NBUF + 16;
+  static_assert(RG == 32 || RG == 48 || RG == 64, "outputs per thread: one x32, x32 + x16 or x64 tcgen05.ld");
+  static_assert(kR % 32 == 0 && ((kPitch / 4) & 1) == 1, "rows are whole 32-column units; the pitch is an odd number of chunks");
+  static_assert(32 * (kCW * RC + 4 * RH) <= kLaunchRegs * kNT, "register file");
+  static_assert(RC % 8 == 0 && RH % 8 == 0, "setmaxnreg takes multiples of 8");
+  static_assert(B_COUNT * 8 <= 192, "mbarriers");
+  // largest tap offset group g serves from TMEM: its RG columns start at offset + RG * g and must end inside the row
+  __host__ __device__ static constexpr int near_max(int g) { return kCols - RG * (g + 1); }
+};
 
 // ---- tensor-memory primitives -------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc_all(uint32_t* slot) {
@@ -115,17 +138,42 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 #define VND_IO16(v, i) VND_IO4(v, i), VND_IO4(v, i + 4), VND_IO4(v, i + 8), VND_IO4(v, i + 12)
 #define VND_I4(v, i) "f"(v[i].x), "f"(v[i].y), "f"(v[i].z), "f"(v[i].w)
 
-// 16 consecutive columns of this thread's TMEM lane, starting at column (taddr & 0xffff).
-template <int O>
-__device__ __forceinline__ void tmem_ld16(float (&v)[kRG], uint32_t taddr) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-               : VND_O16(v, O)
-               : "r"(taddr));
+// N consecutive columns of this thread's TMEM lane, starting at column (taddr & 0xffff), into v[O .. O + N).
+template <int N, int O, int RG>
+__device__ __forceinline__ void tmem_ld(float (&v)[RG], uint32_t taddr) {
+  static_assert(N == 16 || N == 32 || N == 64, "tcgen05.ld.32x32b.x16 / .x32 / .x64");
+  static_assert(O + N <= RG, "destination range");
+  if constexpr (N == 16) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : VND_O16(v, O)
+                 : "r"(taddr));
+  } else if constexpr (N == 32) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : VND_O16(v, O), VND_O16(v, O + 16)
+        : "r"(taddr));
+  } else {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+        "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,"
+        "%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+        : VND_O16(v, O), VND_O16(v, O + 16), VND_O16(v, O + 32), VND_O16(v, O + 48)
+        : "r"(taddr));
+  }
 }
 // The loaded registers are only defined after the wait; naming them as in/out operands keeps the
 // compiler from moving their consumers above it.
-__device__ __forceinline__ void tmem_wait_ld(float (&v)[kRG]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" : VND_IO16(v, 0), VND_IO16(v, 16)::"memory");
+template <int RG>
+__device__ __forceinline__ void tmem_wait_ld(float (&v)[RG]) {
+  if constexpr (RG == 32) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : VND_IO16(v, 0), VND_IO16(v, 16)::"memory");
+  } else if constexpr (RG == 48) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : VND_IO16(v, 0), VND_IO16(v, 16), VND_IO16(v, 32)::"memory");
+  } else {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : VND_IO16(v, 0), VND_IO16(v, 16), VND_IO16(v, 32), VND_IO16(v, 48)::"memory");
+  }
 }
 // 32 consecutive columns written from eight float4.
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float4 (&v)[8]) {
@@ -193,13 +241,13 @@ VND_PACKED_OP(sub2, "sub")
 VND_PACKED_OP(mul2, "mul")
 
 struct TmParams {
-  // TMA descriptors of x and y seen as (96 samples, rows, channels).  The boxes are 100 wide: the four
+  // TMA descriptors of x and y seen as (R samples, rows, channels).  The boxes are R + 4 wide: the four
   // out-of-bounds elements per row are zero-filled on load and clipped on store, which gives the
-  // 100-word row pitch in shared memory with ONE request per tile instead of one per row.
+  // padded row pitch in shared memory with ONE request per tile instead of one per row.
   alignas(64) CUtensorMap tmx;
   alignas(64) CUtensorMap tmy;
   FirParams f;
-  int nblk;      // 96-sample blocks staged per tile (tile + halo)
+  int nblk;      // R-sample blocks staged per tile (tile + halo)
   int opstride;  // words reserved for the program and for each decoded list
   int stagger_ns;  // start-of-run delay between lane quarters (see stagger())
   int tiles_per_run;
@@ -208,18 +256,23 @@ struct TmParams {
   int tiles_per_channel;  // interior tiles
 };
 
-// A tap served from tensor memory: one 32-column load, then 16 packed adds (or subtracts).
-__device__ __forceinline__ void near_issue(float (&t)[kRG], uint32_t tcol) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : VND_O16(t, 0), VND_O16(t, 16)
-      : "r"(tcol));
+// A tap served from tensor memory: the thread's RG columns starting at the tap's column, then RG / 2
+// packed adds (or subtracts).
+template <int RG>
+__device__ __forceinline__ void near_issue(float (&t)[RG], uint32_t tcol) {
+  if constexpr (RG == 32) {
+    tmem_ld<32, 0>(t, tcol);
+  } else if constexpr (RG == 48) {
+    tmem_ld<32, 0>(t, tcol);
+    tmem_ld<16, 32>(t, tcol + 32);
+  } else {
+    tmem_ld<64, 0>(t, tcol);
+  }
 }
-template <bool SUB>
-__device__ __forceinline__ void near_add(const float (&t)[kRG], float (&acc)[kRG]) {
+template <bool SUB, int RG>
+__device__ __forceinline__ void near_add(const float (&t)[RG], float (&acc)[RG]) {
 #pragma unroll
-  for (int j = 0; j < kNP; ++j) {
+  for (int j = 0; j < RG / 2; ++j) {
     if constexpr (SUB) sub2(acc[2 * j], acc[2 * j + 1], t[2 * j], t[2 * j + 1]);
     else add2(acc[2 * j], acc[2 * j + 1], t[2 * j], t[2 * j + 1]);
   }
@@ -228,21 +281,21 @@ __device__ __forceinline__ void near_add(const float (&t)[kRG], float (&acc)[kRG
 // A tap served from shared memory.  `row` is the shared-memory address of the staged block of this thread's row.  The
 // operation word (build_ops) carries the word offset of the aligned 16-byte chunk that holds the
 // thread's first operand, the operand's position A inside it and kx, the number of chunks before the
-// run crosses into the next block, where the pitch inserts a 4-word gap (kx >= 9: no crossing).
-// The 32 operands lie in 8 (A == 0) or 9 chunks.
+// run crosses into the next block, where the pitch inserts a 4-word gap (kx >= chunks of the tap: no crossing).
+// The RG operands lie in RG / 4 (A == 0) or RG / 4 + 1 chunks.
 // The chunks are read with explicit 16-byte loads: left to the compiler, the partly used first and last
 // chunk become 4- and 8-byte loads, which cost as many shared-memory wavefronts each as the full chunk
-// (lanes are 100 words apart: a 4-way conflict for LDS.32, 2-way for LDS.64) and up to twice together.
+// (lanes are a pitch apart: a 4-way conflict for LDS.32, 2-way for LDS.64) and up to twice together.
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
-template <int A, bool SUB>
-__device__ __forceinline__ void far_tap_a(uint32_t row, int op, float (&acc)[kRG]) {
-  constexpr int NC = (A == 0) ? 8 : 9;
+template <int A, bool SUB, int RG>
+__device__ __forceinline__ void far_tap_a(uint32_t row, int op, float (&acc)[RG]) {
+  constexpr int NC = RG / 4 + ((A == 0) ? 0 : 1);
   const uint32_t p = row + 4u * (uint32_t)(op & 0xffff);  // `row`: shared-memory address of the thread's row
-  const int kx = (op >> 16) & 15;
+  const int kx = (op >> 16) & 31;
   float4 c[NC];
   if (kx >= NC) {
 #pragma unroll
@@ -261,23 +314,23 @@ __device__ __forceinline__ void far_tap_a(uint32_t row, int op, float (&acc)[kRG
   }
   if constexpr (A % 2 == 0) {  // operands arrive as aligned register pairs
 #pragma unroll
-    for (int j = 0; j < kNP; ++j) {
+    for (int j = 0; j < RG / 2; ++j) {
       if constexpr (SUB) sub2(acc[2 * j], acc[2 * j + 1], t[2 * j + A], t[2 * j + 1 + A]);
       else add2(acc[2 * j], acc[2 * j + 1], t[2 * j + A], t[2 * j + 1 + A]);
     }
   } else {  // odd shift: the pairs of the loaded data straddle the accumulator pairs -> scalar adds
 #pragma unroll
-    for (int r = 0; r < kRG; ++r) acc[r] = SUB ? fsub(acc[r], t[r + A]) : fadd(acc[r], t[r + A]);
+    for (int r = 0; r < RG; ++r) acc[r] = SUB ? fsub(acc[r], t[r + A]) : fadd(acc[r], t[r + A]);
   }
 }
 
-// Tap operations, decoded once per run for each of the three thread groups (begin_run):
+// Tap operations, decoded once per run for each thread group (begin_run):
 //   near tap: the tap offset i itself (>= 0): the TMEM column is tcol0 + i
 //   far tap:  kOpFar | A << 24 | kx << 16 | word offset of the first chunk relative to the thread's row
 constexpr int kOpFar = (int)0x80000000u;
 
-template <bool SUB>
-__device__ __forceinline__ void far_tap(uint32_t row, int op, float (&acc)[kRG]) {
+template <bool SUB, int RG>
+__device__ __forceinline__ void far_tap(uint32_t row, int op, float (&acc)[RG]) {
   switch ((op >> 24) & 3) {
     case 0: far_tap_a<0, SUB>(row, op, acc); break;
     case 1: far_tap_a<1, SUB>(row, op, acc); break;
@@ -287,10 +340,10 @@ __device__ __forceinline__ void far_tap(uint32_t row, int op, float (&acc)[kRG])
 }
 
 // One tap: from tensor memory (op >= 0) or from shared memory.
-template <bool SUB, bool ALLFAR>
-__device__ __forceinline__ void one_tap(int op, uint32_t tcol0, uint32_t row, float (&acc)[kRG]) {
+template <bool SUB, bool ALLFAR, int RG>
+__device__ __forceinline__ void one_tap(int op, uint32_t tcol0, uint32_t row, float (&acc)[RG]) {
   if (!ALLFAR && op >= 0) {
-    float t[kRG];
+    float t[RG];
     near_issue(t, tcol0 + (uint32_t)op);
     tmem_wait_ld(t);
     near_add<SUB>(t, acc);
@@ -306,17 +359,41 @@ __device__ __forceinline__ void one_tap(int op, uint32_t tcol0, uint32_t row, fl
 // The loops are unrolled by two with the operation words in alternating registers, so that each word
 // is loaded a whole tap before it is needed and never copied (a single loop-carried register made
 // ptxas copy the loaded word at once and stall on the shared-memory latency at every tap).
-template <bool SUB, bool ALLFAR>
-__device__ __forceinline__ void tap_list(const int* __restrict__ ops, int n, int nn, uint32_t tcol0, uint32_t row,
-                                         float (&acc)[kRG]) {
+template <bool SUB, bool ALLFAR, bool PIPE, int RG>
+__device__ __forceinline__ void tap_list(const int* __restrict__ ops, int n, int nn, uint32_t tcol0, uint32_t row, float (&acc)[RG]) {
   if (n <= 0) return;
   int k = 0;
   int op_a = ops[0];
-  if constexpr (!ALLFAR) {
+  if constexpr (!ALLFAR && PIPE) {
+    // Two operand buffers with fixed roles: the load of tap k + 1 is issued right after the wait for tap k, so its
+    // latency runs under the adds of tap k.  tcgen05.wait::ld waits for every outstanding load of the thread, hence
+    // exactly one load is in flight at each wait.
+    if (nn > 0) {
+      float ta[RG], tb[RG];
+      near_issue(ta, tcol0 + (uint32_t)op_a);
+      for (; k + 1 < nn; k += 2) {
+        const int op_b = ops[k + 1];
+        const int op_c = ops[k + 2];  // slack words follow the lists
+        tmem_wait_ld(ta);
+        near_issue(tb, tcol0 + (uint32_t)op_b);
+        near_add<SUB>(ta, acc);
+        tmem_wait_ld(tb);
+        if (k + 2 < nn) near_issue(ta, tcol0 + (uint32_t)op_c);
+        near_add<SUB>(tb, acc);
+      }
+      if (k < nn) {
+        tmem_wait_ld(ta);
+        near_add<SUB>(ta, acc);
+        ++k;
+      }
+      if (k >= n) return;
+      op_a = ops[k];
+    }
+  } else if constexpr (!ALLFAR) {
     for (; k < nn; k += 2) {  // near prefix
       const int op_b = ops[k + 1];  // two words of slack follow the lists, so the prefetches stay in bounds
       {
-        float t[kRG];
+        float t[RG];
         near_issue(t, tcol0 + (uint32_t)op_a);
         tmem_wait_ld(t);
         near_add<SUB>(t, acc);
@@ -328,7 +405,7 @@ __device__ __forceinline__ void tap_list(const int* __restrict__ ops, int n, int
         break;
       }
       {
-        float t[kRG];
+        float t[RG];
         near_issue(t, tcol0 + (uint32_t)op_b);
         tmem_wait_ld(t);
         near_add<SUB>(t, acc);
@@ -349,66 +426,72 @@ __device__ __forceinline__ void tap_list(const int* __restrict__ ops, int n, int
 // Segments [s0, s1) of the program added into the running output, in the reference's order
 // (decorrelation.py:402-414): acc = 0; acc -= x[n + i] over the negative list; acc += x[n + i] over
 // the positive list; acc *= gain; y += acc.
-template <bool ALLFAR>
+template <bool ALLFAR, bool PIPE, int RG>
 __device__ __forceinline__ void run_segments(const int4* __restrict__ segtab, int s0, int s1, const int*& ops, uint32_t tcol0, uint32_t row,
-                                             float (&yv)[kRG]) {
+                                             float (&yv)[RG]) {
   for (int s = s0; s < s1; ++s) {
     const int4 d = segtab[s];  // x = negative taps, y = positive taps, z = leading tensor-memory taps of both lists, w = gain bits
     const int n_neg = d.x, n_pos = d.y;
-    float acc[kRG];
+    float acc[RG];
 #pragma unroll
-    for (int r = 0; r < kRG; ++r) acc[r] = 0.0f;
+    for (int r = 0; r < RG; ++r) acc[r] = 0.0f;
     const int nn = ALLFAR ? 0 : d.z;  // leading tensor-memory taps: neg list in the low half, pos list in the high half
-    tap_list<true, ALLFAR>(ops, n_neg, nn & 0xffff, tcol0, row, acc);
-    tap_list<false, ALLFAR>(ops + n_neg, n_pos, nn >> 16, tcol0, row, acc);
+    tap_list<true, ALLFAR, PIPE>(ops, n_neg, nn & 0xffff, tcol0, row, acc);
+    tap_list<false, ALLFAR, PIPE>(ops + n_neg, n_pos, nn >> 16, tcol0, row, acc);
     ops += n_neg + n_pos;
     {  // 1.0f when the program carries no gains (x * 1 == x bit for bit)
       const float gain = __int_as_float(d.w);
 #pragma unroll
-      for (int j = 0; j < kNP; ++j) mul2(acc[2 * j], acc[2 * j + 1], gain, gain);
+      for (int j = 0; j < RG / 2; ++j) mul2(acc[2 * j], acc[2 * j + 1], gain, gain);
     }
     if (s == 0) {  // the reference adds into zeros (a -0 partial sum becomes +0)
 #pragma unroll
-      for (int j = 0; j < kNP; ++j) {
+      for (int j = 0; j < RG / 2; ++j) {
         yv[2 * j] = acc[2 * j];
         yv[2 * j + 1] = acc[2 * j + 1];
         add2(yv[2 * j], yv[2 * j + 1], 0.0f, 0.0f);
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < kNP; ++j) add2(yv[2 * j], yv[2 * j + 1], acc[2 * j], acc[2 * j + 1]);
+      for (int j = 0; j < RG / 2; ++j) add2(yv[2 * j], yv[2 * j + 1], acc[2 * j], acc[2 * j + 1]);
     }
   }
 }
 
-// Dynamic shared memory: [0,112) mbarriers | [192,196) TMEM base | [196,200) first all-far segment |
-//   [256, ...) float in[3][nblk][100] | float stage[128][100] | int program[] | int ops[3][] | int4 segtab[]
+// Dynamic shared memory: [0,192) mbarriers | [192,196) TMEM base | [196,212) first all-far segment per group |
+//   [256, ...) float in[NBUF][nblk][pitch] | float stage[128][pitch] | int program[] | int ops[G][] | int4 segtab[G][]
 // The role functions rebuild their pointers from this symbol so that every access stays in the
 // shared address space (LDS/STS, not generic loads).
 extern __shared__ __align__(128) unsigned char tm_smem[];
 
+template <class T>
 struct Smem {
   uint64_t* bars;
-  int* s_near_end;
+  int* s_near_end;  // [G]
   float* in_all;
   float* stage;
   int* sprog;
-  int* ops;  // [3][opstride]: decoded tap operations per thread group
-  int4* segtab;  // per segment: taps of the negative and positive list, their leading tensor-memory taps, gain bits
+  int* ops;  // [G][opstride]: decoded tap operations per thread group
+  int4* segtab;  // [G][opstride / 2]: per segment: taps of the negative and positive list, their leading tensor-memory taps, gain bits
   int bufw;
   int opstride;
   __device__ __forceinline__ explicit Smem(const TmParams& P) {
     bars = reinterpret_cast<uint64_t*>(tm_smem);
     s_near_end = reinterpret_cast<int*>(tm_smem + 196);
     in_all = reinterpret_cast<float*>(tm_smem + kBarBytes);
-    bufw = (P.nblk * kPitch + 31) & ~31;  // TMA tensor copies want 128-byte aligned shared-memory addresses
-    stage = in_all + kNBuf * bufw;
-    sprog = reinterpret_cast<int*>(stage + kRows * kPitch);
+    bufw = (P.nblk * T::kPitch + 31) & ~31;  // TMA tensor copies want 128-byte aligned shared-memory addresses
+    stage = in_all + T::kNBuf * bufw;
+    sprog = reinterpret_cast<int*>(stage + kRows * T::kPitch);
     opstride = P.opstride;
     ops = sprog + opstride;
-    segtab = reinterpret_cast<int4*>(ops + kG * opstride);  // opstride is a multiple of 4 words: 16-byte aligned
+    segtab = reinterpret_cast<int4*>(ops + T::kG * opstride);  // opstride is a multiple of 4 words: 16-byte aligned
   }
+  __device__ __forceinline__ const int4* segtab_of(int g) const { return segtab + g * (opstride / 2); }  // 2 * opstride words per group
 };
+template <class T>
+constexpr size_t tm_tail_words(int opstride) {  // program + decoded lists + segment tables
+  return (size_t)(1 + T::kG + 2 * T::kG) * opstride;
+}
 
 struct RunInfo {
   int c, first_tile, n_tiles, nprog;
@@ -417,7 +500,8 @@ struct RunInfo {
 // Per-run prologue shared by both roles (every thread of the CTA takes part): decode the run, copy
 // the unfiltered channel through or load and decode the channel's program.  Returns false for a
 // copied run.
-__device__ __forceinline__ bool begin_run(const TmParams& P, const Smem& sm, int run, int tid, RunInfo& r) {
+template <class T>
+__device__ __forceinline__ bool begin_run(const TmParams& P, const Smem<T>& sm, int run, int tid, RunInfo& r) {
   const FirParams& p = P.f;
   r.c = run / P.runs_per_channel;
   r.first_tile = (run % P.runs_per_channel) * P.tiles_per_run;
@@ -428,46 +512,48 @@ __device__ __forceinline__ bool begin_run(const TmParams& P, const Smem& sm, int
   if (r.nprog == 0) {  // unfiltered channel: copy through (decorrelation.py:399-400)
     const float* xc = reinterpret_cast<const float*>(p.x) + (long long)r.c * p.x_sc;
     float* yc = p.y + (long long)r.c * p.y_sc;
-    const long long t_begin = (long long)r.first_tile * kTile, t_end = t_begin + (long long)r.n_tiles * kTile;
-    for (long long t = t_begin + 4 * tid; t < t_end; t += 4 * kNT)
+    const long long t_begin = (long long)r.first_tile * T::kTile, t_end = t_begin + (long long)r.n_tiles * T::kTile;
+    for (long long t = t_begin + 4 * tid; t < t_end; t += 4 * T::kNT)
       *reinterpret_cast<float4*>(yc + t) = *reinterpret_cast<const float4*>(xc + t);
     return false;
   }
   __syncthreads();  // the pipeline of the previous run has drained: program, buffers and TMEM are free
-  for (int i = tid; i < r.nprog; i += kNT) sm.sprog[i] = p.words[w0 + i];
+  for (int i = tid; i < r.nprog; i += T::kNT) sm.sprog[i] = p.words[w0 + i];
   __syncthreads();
   const int S = sm.sprog[0];
   const int* taps = sm.sprog + 1 + 3 * S;
   const int ntaps = r.nprog - 1 - 3 * S;
-  if (tid == 0) {  // segments from this one on have no tap inside the TMEM window
+  if (tid < T::kG) {  // per thread group: the segment table; segments from near_end on have no tap inside the group's TMEM reach
+    const int g = tid, nmax = T::near_max(g);
+    int4* st = sm.segtab + g * (sm.opstride / 2);
     const int* tq = taps;
     int ne = 0;
     for (int s = 0; s < S; ++s) {
       const int n_neg = sm.sprog[1 + 3 * s], n = n_neg + sm.sprog[2 + 3 * s];
       for (int k = 0; k < n; ++k)
-        if (tq[k] <= kNearMax) ne = s + 1;
+        if (tq[k] <= nmax) ne = s + 1;
       int a = 0, b = 0;  // leading tensor-memory taps of the two lists
-      while (a < n_neg && tq[a] <= kNearMax) ++a;
-      while (n_neg + b < n && tq[n_neg + b] <= kNearMax) ++b;
-      sm.segtab[s] = make_int4(n_neg, n - n_neg, a | (b << 16), p.apply_gain ? sm.sprog[3 + 3 * s] : __float_as_int(1.0f));
+      while (a < n_neg && tq[a] <= nmax) ++a;
+      while (n_neg + b < n && tq[n_neg + b] <= nmax) ++b;
+      st[s] = make_int4(n_neg, n - n_neg, a | (b << 16), p.apply_gain ? sm.sprog[3 + 3 * s] : __float_as_int(1.0f));
       tq += n;
     }
-    *sm.s_near_end = ne;
+    sm.s_near_end[g] = ne;
   }
-  // decode the taps for the three thread groups (group g owns outputs 32 g .. 32 g + 31 of a row)
-  for (int t = tid; t < kG * (ntaps + 2); t += kNT) {
+  // decode the taps for the thread groups (group g owns outputs RG g .. RG g + RG - 1 of a row)
+  for (int t = tid; t < T::kG * (ntaps + 2); t += T::kNT) {
     const int g = t / (ntaps + 2), k = t - g * (ntaps + 2);
     int op = 0;  // two slack words behind each list
     if (k < ntaps) {
       const int i = taps[k];
-      if (i <= kNearMax) {
+      if (i <= T::near_max(g)) {
         op = i;
       } else {
-        const int o = i + kRG * g, A = o & 3, oal = o - A;
-        const int blk = oal / kR, w = oal - blk * kR;
-        int kx = (kR - w) >> 2;
-        if (kx > 9) kx = 9;
-        op = kOpFar | (A << 24) | (kx << 16) | (blk * kPitch + w);
+        const int o = i + T::kRG * g, A = o & 3, oal = o - A;
+        const int blk = oal / T::kR, w = oal - blk * T::kR;
+        int kx = (T::kR - w) >> 2;
+        if (kx > 31) kx = 31;
+        op = kOpFar | (A << 24) | (kx << 16) | (blk * T::kPitch + w);
       }
     }
     sm.ops[g * sm.opstride + k] = op;
@@ -488,16 +574,17 @@ __device__ __forceinline__ void stagger(int q, int ns) {
 }
 
 // ---------------------------------------------------------------- data-movement warp of lane quarter q
-// One elected lane per warp: quarter 0 issues the tile loads (one TMA request per tile, three tiles
+// One elected lane per warp: quarter 0 issues the tile loads (one TMA request per tile, NBUF - 1 tiles
 // ahead), every quarter stores its own 32 staged rows (one request per tile).
+template <class T>
 __device__ __noinline__ void helper_main(const TmParams& P, uint32_t tbase, int tid) {
-  const Smem sm(P);
+  const Smem<T> sm(P);
   const int nblk = P.nblk, n_runs = P.n_runs, stagger_ns = P.stagger_ns;  // P lives behind a generic pointer here
   const int lane = tid & 31, q = (tid >> 5) & 3;
   const int m = 32 * q + lane;
   const uint32_t bars = smem_u32(sm.bars), in0 = smem_u32(sm.in_all), buf_bytes = (uint32_t)sm.bufw * 4u;
-  const uint32_t stage_q = smem_u32(sm.stage + 32 * q * kPitch);
-  const uint32_t tx_bytes = (uint32_t)nblk * (kPitch * 4u);  // the whole box counts, zero-filled columns included
+  const uint32_t stage_q = smem_u32(sm.stage + 32 * q * T::kPitch);
+  const uint32_t tx_bytes = (uint32_t)nblk * (T::kPitch * 4u);  // the whole box counts, zero-filled columns included
   const void* tmx = &P.tmx;
   const void* tmy = &P.tmy;
   const bool loader = q == 0 && lane == 0;
@@ -506,36 +593,36 @@ __device__ __noinline__ void helper_main(const TmParams& P, uint32_t tbase, int 
   unsigned tpar = 0;           // parity of the tile counter (TMEM and staging barriers)
   for (int run = blockIdx.x; run < n_runs; run += gridDim.x) {
     RunInfo r;
-    if (!begin_run(P, sm, run, tid, r)) continue;
+    if (!begin_run<T>(P, sm, run, tid, r)) continue;
     stagger(q, stagger_ns);
-    int load_row = r.first_tile * kRows;  // first row (96 samples) of the next tile to load
+    int load_row = r.first_tile * kRows;  // first row (R samples) of the next tile to load
     int store_row = r.first_tile * kRows + 32 * q;
     int to_load = r.n_tiles;
 #define VND_ISSUE_LOAD()                                                                   \
   do {                                                                                     \
     if (loader) {                                                                          \
-      mbar_wait_u32(bars + 8u * (B_IN_FREE + lb), lpar); /* every warp is done with the tile that was there */ \
-      const uint32_t full = bars + 8u * (B_IN_FULL + lb);                                  \
+      mbar_wait_u32(bars + 8u * (T::B_IN_FREE + lb), lpar); /* every warp is done with the tile that was there */ \
+      const uint32_t full = bars + 8u * (T::B_IN_FULL + lb);                               \
       mbar_expect_tx_u32(full, tx_bytes);                                                  \
       fence_proxy_async();                                                                 \
       tma_load_3d(in0 + (uint32_t)lb * buf_bytes, tmx, 0, load_row, r.c, full);            \
     }                                                                                      \
     load_row += kRows;                                                                     \
     --to_load;                                                                             \
-    if (++lb == kNBuf) {                                                                   \
+    if (++lb == T::kNBuf) {                                                                \
       lb = 0;                                                                              \
       lpar ^= 1u;                                                                          \
     }                                                                                      \
   } while (0)
-    for (int d = 0; d < kNBuf - 1 && to_load > 0; ++d) VND_ISSUE_LOAD();
+    for (int d = 0; d < T::kNBuf - 1 && to_load > 0; ++d) VND_ISSUE_LOAD();
     for (int ti = 0; ti < r.n_tiles; ++ti) {
-      mbar_wait_u32(bars + 8u * (B_IN_FULL + fb), fpar);
+      mbar_wait_u32(bars + 8u * (T::B_IN_FULL + fb), fpar);
       VND_TRACE(ti, 4);
-      mbar_wait_u32(bars + 8u * (B_TM_FREE + q), tpar ^ 1u);  // the quarter is past its last TMEM tap of the previous tile
+      mbar_wait_u32(bars + 8u * (T::B_TM_FREE + q), tpar ^ 1u);  // the quarter is past its last TMEM tap of the previous tile
       tmem_fence_after();
       VND_TRACE(ti, 0);
-      {  // fill row m: 32 columns per step; a block of 96 samples is three steps, then the pitch skips 4 words
-        const float4* src = reinterpret_cast<const float4*>(sm.in_all + fb * sm.bufw + m * kPitch);
+      {  // fill row m: 32 columns per step; a block of R samples is R / 32 steps, then the pitch skips 4 words
+        const float4* src = reinterpret_cast<const float4*>(sm.in_all + fb * sm.bufw + m * T::kPitch);
         uint32_t tcol = tbase;
         int sub = 0;
 #pragma unroll 1
@@ -546,7 +633,7 @@ __device__ __noinline__ void helper_main(const TmParams& P, uint32_t tbase, int 
           tmem_st32(tcol, v);
           tcol += 32;
           src += 8;
-          if (++sub == 3) {
+          if (++sub == T::kUnitsPerBlock) {
             sub = 0;
             src += 1;
           }
@@ -557,20 +644,20 @@ __device__ __noinline__ void helper_main(const TmParams& P, uint32_t tbase, int 
       __syncwarp();
       VND_TRACE(ti, 1);
       if (lane == 0) {
-        mbar_arrive_u32(bars + 8u * (B_TM_FULL + q));
-        mbar_arrive_u32(bars + 8u * (B_IN_FREE + fb));
+        mbar_arrive_u32(bars + 8u * (T::B_TM_FULL + q));
+        mbar_arrive_u32(bars + 8u * (T::B_IN_FREE + fb));
       }
-      if (++fb == kNBuf) {
+      if (++fb == T::kNBuf) {
         fb = 0;
         fpar ^= 1u;
       }
       if (to_load > 0) VND_ISSUE_LOAD();
       if (ti > 0 && lane == 0) {  // the previous tile's 32 rows of this quarter
-        mbar_wait_u32(bars + 8u * (B_ST_FULL + q), tpar ^ 1u);
+        mbar_wait_u32(bars + 8u * (T::B_ST_FULL + q), tpar ^ 1u);
         tma_store_3d(tmy, 0, store_row, r.c, stage_q);
         bulk_commit();
         bulk_wait_read0();
-        mbar_arrive_u32(bars + 8u * (B_ST_FREE + q));
+        mbar_arrive_u32(bars + 8u * (T::B_ST_FREE + q));
       }
       if (ti > 0) store_row += kRows;
       __syncwarp();
@@ -579,67 +666,70 @@ __device__ __noinline__ void helper_main(const TmParams& P, uint32_t tbase, int 
     }
 #undef VND_ISSUE_LOAD
     if (lane == 0) {
-      mbar_wait_u32(bars + 8u * (B_ST_FULL + q), tpar ^ 1u);
+      mbar_wait_u32(bars + 8u * (T::B_ST_FULL + q), tpar ^ 1u);
       tma_store_3d(tmy, 0, store_row, r.c, stage_q);
       bulk_commit();
       bulk_wait_read0();
-      mbar_arrive_u32(bars + 8u * (B_ST_FREE + q));
+      mbar_arrive_u32(bars + 8u * (T::B_ST_FREE + q));
     }
     __syncwarp();
   }
 }
 
 // ---------------------------------------------------------------- compute warp (q, g)
+template <class T>
 __device__ __noinline__ void compute_main(const TmParams& P, uint32_t tbase, int tid) {
-  const Smem sm(P);
+  constexpr int RG = T::kRG;
+  const Smem<T> sm(P);
   const int n_runs = P.n_runs, stagger_ns = P.stagger_ns;  // P lives behind a generic pointer here
   const int lane = tid & 31, warp = tid >> 5;
   const int q = warp & 3, g = warp >> 2;
   const int m = 32 * q + lane;
   uint64_t* bars = sm.bars;
-  const uint32_t tcol0 = tbase + (uint32_t)(kRG * g);  // column of this thread's first output
+  const uint32_t tcol0 = tbase + (uint32_t)(RG * g);  // column of this thread's first output
+  const int4* segtab = sm.segtab_of(g);
   int b = 0;           // ring slot of the current tile
   unsigned fpar = 0;   // in_full parity of slot b
   unsigned tpar = 0;   // parity of the tile counter (TMEM and staging barriers)
   for (int run = blockIdx.x; run < n_runs; run += gridDim.x) {
     RunInfo r;
-    if (!begin_run(P, sm, run, tid, r)) continue;
+    if (!begin_run<T>(P, sm, run, tid, r)) continue;
     stagger(q, stagger_ns);
     const int S = sm.sprog[0];
-    const int near_end = *sm.s_near_end;
+    const int near_end = sm.s_near_end[g];
     for (int ti = 0; ti < r.n_tiles; ++ti) {
-      const uint32_t row = smem_u32(sm.in_all + b * sm.bufw + m * kPitch);
-      float yv[kRG];
+      const uint32_t row = smem_u32(sm.in_all + b * sm.bufw + m * T::kPitch);
+      float yv[RG];
 #pragma unroll
-      for (int rr = 0; rr < kRG; ++rr) yv[rr] = 0.0f;
+      for (int rr = 0; rr < RG; ++rr) yv[rr] = 0.0f;
       const int* ops = sm.ops + g * sm.opstride;
       VND_TRACE(ti, 0);
-      mbar_wait(&bars[B_IN_FULL + b], fpar);
-      mbar_wait(&bars[B_TM_FULL + q], tpar);
+      mbar_wait(&bars[T::B_IN_FULL + b], fpar);
+      mbar_wait(&bars[T::B_TM_FULL + q], tpar);
       tmem_fence_after();
       VND_TRACE(ti, 1);
-      run_segments<false>(sm.segtab, 0, near_end, ops, tcol0, row, yv);
+      run_segments<false, T::kPipe>(segtab, 0, near_end, ops, tcol0, row, yv);
       VND_TRACE(ti, 2);
       tmem_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[B_TM_FREE + q]);  // the helper may fill TMEM for the next tile
-      run_segments<true>(sm.segtab, near_end, S, ops, tcol0, row, yv);
+      if (lane == 0) mbar_arrive(&bars[T::B_TM_FREE + q]);  // the helper may fill TMEM for the next tile
+      run_segments<true, false>(segtab, near_end, S, ops, tcol0, row, yv);
       VND_TRACE(ti, 3);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[B_IN_FREE + b]);  // this warp is done with the tile buffer
-      mbar_wait(&bars[B_ST_FREE + q], tpar ^ 1u);
+      if (lane == 0) mbar_arrive(&bars[T::B_IN_FREE + b]);  // this warp is done with the tile buffer
+      mbar_wait(&bars[T::B_ST_FREE + q], tpar ^ 1u);
       VND_TRACE(ti, 5);  // the previous tile's stores have read the staging rows
       {
-        float4* dst = reinterpret_cast<float4*>(sm.stage + m * kPitch + kRG * g);
+        float4* dst = reinterpret_cast<float4*>(sm.stage + m * T::kPitch + RG * g);
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) dst[jj] = make_float4(yv[4 * jj], yv[4 * jj + 1], yv[4 * jj + 2], yv[4 * jj + 3]);
+        for (int jj = 0; jj < RG / 4; ++jj) dst[jj] = make_float4(yv[4 * jj], yv[4 * jj + 1], yv[4 * jj + 2], yv[4 * jj + 3]);
       }
       fence_proxy_async();
       __syncwarp();
       VND_TRACE(ti, 4);
-      if (lane == 0) mbar_arrive(&bars[B_ST_FULL + q]);
+      if (lane == 0) mbar_arrive(&bars[T::B_ST_FULL + q]);
       tpar ^= 1u;
-      if (++b == kNBuf) {
+      if (++b == T::kNBuf) {
         b = 0;
         fpar ^= 1u;
       }
@@ -647,22 +737,23 @@ __device__ __noinline__ void compute_main(const TmParams& P, uint32_t tbase, int
   }
 }
 
-__global__ void __launch_bounds__(kNT, 1) fir_tmem_kernel(const __grid_constant__ TmParams P) {
-  const Smem sm(P);
+template <class T>
+__global__ void __launch_bounds__(T::kNT, 1) fir_tmem_kernel(const __grid_constant__ TmParams P) {
+  const Smem<T> sm(P);
   uint32_t* tm_slot = reinterpret_cast<uint32_t*>(tm_smem + 192);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   if (tid == 0) {
-    for (int b = 0; b < kNBuf; ++b) {
-      mbar_init(&sm.bars[B_IN_FULL + b], 1);
-      mbar_init(&sm.bars[B_IN_FREE + b], kCW + 4);
+    for (int b = 0; b < T::kNBuf; ++b) {
+      mbar_init(&sm.bars[T::B_IN_FULL + b], 1);
+      mbar_init(&sm.bars[T::B_IN_FREE + b], T::kCW + 4);
     }
     for (int k = 0; k < 4; ++k) {
-      mbar_init(&sm.bars[B_ST_FULL + k], kG);
-      mbar_init(&sm.bars[B_ST_FREE + k], 1);
-      mbar_init(&sm.bars[B_TM_FULL + k], 1);
-      mbar_init(&sm.bars[B_TM_FREE + k], kG);
+      mbar_init(&sm.bars[T::B_ST_FULL + k], T::kG);
+      mbar_init(&sm.bars[T::B_ST_FREE + k], 1);
+      mbar_init(&sm.bars[T::B_TM_FULL + k], 1);
+      mbar_init(&sm.bars[T::B_TM_FREE + k], T::kG);
     }
     mbar_fence_init();
   }
@@ -671,12 +762,12 @@ __global__ void __launch_bounds__(kNT, 1) fir_tmem_kernel(const __grid_constant_
   __syncthreads();
   tmem_fence_after();
   const uint32_t tbase = *tm_slot + ((uint32_t)(32 * (warp & 3)) << 16);
-  if (warp >= kCW) {
-    set_max_regs_dec<kRegsHelper>();
-    helper_main(P, tbase, tid);
+  if (warp >= T::kCW) {
+    set_max_regs_dec<T::kRegsHelper>();
+    helper_main<T>(P, tbase, tid);
   } else {
-    set_max_regs_inc<kRegsCompute>();
-    compute_main(P, tbase, tid);
+    set_max_regs_inc<T::kRegsCompute>();
+    compute_main<T>(P, tbase, tid);
   }
   tmem_fence_before();
   __syncthreads();
@@ -689,6 +780,11 @@ __global__ void __launch_bounds__(kNT, 1) fir_tmem_kernel(const __grid_constant_
 static const int g_stagger_ns = [] {
   const char* e = getenv("VND_TM_STAGGER_NS");
   return e ? atoi(e) : 2000;
+}();
+// VND_TM_SHAPE picks the kernel shape (see TmShape): 0 = 3 x 32, 1 = 2 x 48, 2 = 2 x 64, 3 = 2 x 32.
+static const int g_tm_shape = [] {
+  const char* e = getenv("VND_TM_SHAPE");
+  return e ? atoi(e) : VND_TM_DEFAULT_SHAPE;
 }();
 
 // cuTensorMapEncodeTiled through the runtime (no link against libcuda).
@@ -705,13 +801,13 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// base[c * stride_c + row * 96 + k] as a (96, rows, channels) float32 tensor with a (100, box_rows, 1) box
-static bool encode_rows(CUtensorMap* tm, const void* base, long long frames, long long stride_c, int channels, int box_rows) {
+// base[c * stride_c + row * R + k] as a (R, rows, channels) float32 tensor with a (R + 4, box_rows, 1) box
+static bool encode_rows(CUtensorMap* tm, const void* base, long long frames, long long stride_c, int channels, int box_rows, int R) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return false;
-  const cuuint64_t dims[3] = {(cuuint64_t)kR, (cuuint64_t)(frames / kR), (cuuint64_t)channels};
-  const cuuint64_t strides[2] = {(cuuint64_t)kR * 4u, (cuuint64_t)stride_c * 4u};
-  const cuuint32_t box[3] = {(cuuint32_t)kPitch, (cuuint32_t)box_rows, 1u};
+  const cuuint64_t dims[3] = {(cuuint64_t)R, (cuuint64_t)(frames / R), (cuuint64_t)channels};
+  const cuuint64_t strides[2] = {(cuuint64_t)R * 4u, (cuuint64_t)stride_c * 4u};
+  const cuuint32_t box[3] = {(cuuint32_t)(R + 4), (cuuint32_t)box_rows, 1u};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -720,15 +816,18 @@ static bool encode_rows(CUtensorMap* tm, const void* base, long long frames, lon
 // Runs the interior tiles of every channel and reports the frames covered per channel in
 // *frames_done (a multiple of the tile).  VND_EUNSUPPORTED (no error text) when the request does
 // not qualify; the caller then uses the other kernels for everything.
-int fir_tmem_launch(const FirParams& f, int max_prog_words, cudaStream_t st, long long* frames_done) {
+template <class T>
+static int fir_tmem_launch_t(const FirParams& f, int max_prog_words, cudaStream_t st, long long* frames_done) {
+  constexpr int kR = T::kR, kPitch = T::kPitch, kTile = T::kTile;
   *frames_done = 0;
   if (!f.bulk_ok || f.x_st != 1 || f.y_st != 1) return VND_EUNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(f.y) % 16) != 0 || (f.y_sc % 4) != 0) return VND_EUNSUPPORTED;
   int nblk = kRows + (f.halo + 4 + kR - 1) / kR;
-  if (nblk < kRows + 6) nblk = kRows + 6;  // the TMEM fill reads 512 columns of every row
-  const int opstride = (max_prog_words + 4 + 3) & ~3;  // a multiple of 4 words: the segment table behind the lists stays 16-byte aligned
+  const int fill_blocks = kRows + (kCols + kR - 1) / kR;  // the TMEM fill reads 512 columns of every row
+  if (nblk < fill_blocks) nblk = fill_blocks;
+  const int opstride = (max_prog_words + 4 + 3) & ~3;  // a multiple of 4 words: the segment tables behind the lists stay 16-byte aligned
   const size_t bufw = ((size_t)nblk * kPitch + 31) & ~(size_t)31;
-  const size_t smem = kBarBytes + kNBuf * bufw * 4 + (size_t)kRows * kPitch * 4 + (size_t)(3 + kG) * opstride * 4;
+  const size_t smem = kBarBytes + T::kNBuf * bufw * 4 + (size_t)kRows * kPitch * 4 + tm_tail_words<T>(opstride) * 4;
   if (smem > (size_t)kMaxDynSmem || nblk > 256) return VND_EUNSUPPORTED;  // a TMA box has at most 256 rows
   if (f.channels > 1 && (f.x_sc % 4 != 0 || f.x_sc < f.frames || f.y_sc < f.frames)) return VND_EUNSUPPORTED;
   const long long span = (long long)nblk * kR;  // samples a tile's bulk loads touch
@@ -742,7 +841,7 @@ int fir_tmem_launch(const FirParams& f, int max_prog_words, cudaStream_t st, lon
   P.opstride = opstride;
   P.stagger_ns = g_stagger_ns;
   const long long sx = f.channels > 1 ? f.x_sc : f.frames, sy = f.channels > 1 ? f.y_sc : f.frames;
-  if (!encode_rows(&P.tmx, f.x, f.frames, sx, f.channels, nblk) || !encode_rows(&P.tmy, f.y, f.frames, sy, f.channels, 32))
+  if (!encode_rows(&P.tmx, f.x, f.frames, sx, f.channels, nblk, kR) || !encode_rows(&P.tmy, f.y, f.frames, sy, f.channels, 32, kR))
     return VND_EUNSUPPORTED;  // no tensor-map encoder in this driver: the other kernels take over
   const long long tiles = (f.frames - span) / kTile + 1;
   if (tiles > 0x3fffffffLL / (f.channels > 0 ? f.channels : 1)) return VND_EUNSUPPORTED;
@@ -768,14 +867,25 @@ int fir_tmem_launch(const FirParams& f, int max_prog_words, cudaStream_t st, lon
     P.runs_per_channel = (int)ceil_div<long long>(tiles, P.tiles_per_run);
   }
   P.n_runs = P.runs_per_channel * f.channels;
-  VND_CUDA_OK(cudaFuncSetAttribute(fir_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VND_CUDA_OK(cudaFuncSetAttribute(fir_tmem_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = di.sm_count;
   if (grid > P.n_runs) grid = P.n_runs;
-  fir_tmem_kernel<<<(unsigned)grid, kNT, smem, st>>>(P);
+  fir_tmem_kernel<T><<<(unsigned)grid, T::kNT, smem, st>>>(P);
   rc = after_launch("fir_tmem_kernel");
   if (rc) return rc;
   *frames_done = tiles * kTile;
   return VND_OK;
+}
+
+int fir_tmem_launch(const FirParams& f, int max_prog_words, cudaStream_t st, long long* frames_done) {
+  switch (g_tm_shape) {
+    case 1: return fir_tmem_launch_t<TmShape<2, 48, 3, 200, 104>>(f, max_prog_words, st, frames_done);
+    case 2: return fir_tmem_launch_t<TmShape<2, 64, 2, 216, 72>>(f, max_prog_words, st, frames_done);
+    case 3: return fir_tmem_launch_t<TmShape<2, 32, 3, 200, 104>>(f, max_prog_words, st, frames_done);
+    case 4: return fir_tmem_launch_t<TmShape<2, 48, 3, 224, 56, true>>(f, max_prog_words, st, frames_done);
+    case 5: return fir_tmem_launch_t<TmShape<2, 32, 3, 200, 104, true>>(f, max_prog_words, st, frames_done);
+    default: return fir_tmem_launch_t<TmShape<3, 32, 3, 144, 80>>(f, max_prog_words, st, frames_done);
+  }
 }
 
 }  // namespace vnd

@@ -10,8 +10,13 @@ the same kernels (one candidate).  The kernels return the sums the objective is 
 combination below follows the reference's dtype chain (float32 for velvet-noise candidates, float64
 for Haas candidates).
 
-Brent refinement stays scipy's ``minimize_scalar`` on the host, as in the reference; each of its
-evaluations is one single-candidate kernel call.
+Refinement is the bounded Brent minimiser scipy runs for the reference (``minimize_scalar(method="bounded")``),
+restated as a coroutine (``_bounded_brent``) so that every local minimum - of every clip - advances in lock-step:
+one kernel launch per Brent iteration over all live minimisers instead of one per evaluation.
+
+``optimize_velvet_noise_batch`` runs the whole optimisation for MANY clips (BASELINE config 5): clips are
+partitioned over the ranks of ``torch.distributed`` (one process per GPU), the grid scores are all-gathered as one
+float32 matrix (the only collective on the data path), and each rank refines the local minima of its own clips.
 """
 
 from __future__ import annotations
@@ -29,7 +34,7 @@ from .utils.dsp import EPSILON, LayoutMode
 
 __all__ = [
     "symmetry_aware_objective", "grid_scan", "get_local_minima", "optimize_local_minima", "optimize_haas_delay",
-    "optimize_velvet_noise", "vn_objective_partials", "haas_objective_partials", "vn_scores_from_partials", "haas_scores_from_partials",
+    "optimize_velvet_noise", "optimize_velvet_noise_batch", "vn_objective_partials", "haas_objective_partials", "vn_scores_from_partials", "haas_scores_from_partials",
 ]
 
 _F32_HALF_PI = np.float32(np.pi / 2)
@@ -424,7 +429,8 @@ def _bounded_brent(x1, x2, xatol: float, maxiter: int = 500):
     return OptimizeResult(fun=np.asarray(fx)[()], status=flag, success=(flag == 0), x=xf, nfev=num, nit=num)  # numpy scalar, as minimize_scalar returns it
 
 
-def lockstep_minimize(bounds: Sequence[tuple[float, float]], batch_objective: Callable[[list[float]], Sequence[Any]], *, xatol: float = 1e-4):
+def lockstep_minimize(bounds: Sequence[tuple[float, float]], batch_objective: Callable[..., Sequence[Any]], *, xatol: float = 1e-4,
+                      with_ids: bool = False):
     """Run the bounded Brent minimiser on many intervals at once, in lock-step.
 
     Every interval gets its own minimiser (``_bounded_brent``: the reference's refinement step,
@@ -432,7 +438,9 @@ def lockstep_minimize(bounds: Sequence[tuple[float, float]], batch_objective: Ca
     minimisers are evaluated with ONE call of ``batch_objective`` (one kernel launch over all of them) and handed
     back.  Returns the ``OptimizeResult`` list in input order.  The sequence of abscissae each minimiser sees
     depends only on its own function values, so the results equal those of the one-at-a-time loop whenever
-    ``batch_objective`` returns the values the scalar objective would."""
+    ``batch_objective`` returns the values the scalar objective would.  With ``with_ids`` the callback is called as
+    ``batch_objective(abscissae, ids)`` (``ids`` = positions in ``bounds``), which is how the multi-clip optimiser
+    knows the clip each abscissa belongs to."""
     n = len(bounds)
     results: list[Any] = [None] * n
     live: dict[int, Any] = {}
@@ -443,7 +451,8 @@ def lockstep_minimize(bounds: Sequence[tuple[float, float]], batch_objective: Ca
         pending[i] = next(gen)  # the first abscissa (a minimiser always evaluates at least once)
     while live:
         ids = sorted(live)
-        vals = batch_objective([float(pending[i]) for i in ids])
+        xs = [float(pending[i]) for i in ids]
+        vals = batch_objective(xs, ids) if with_ids else batch_objective(xs)
         for i, v in zip(ids, vals):
             try:
                 pending[i] = live[i].send(v)
@@ -534,3 +543,182 @@ def optimize_velvet_noise(*, input_signal, sample_rate_hz: int, duration_seconds
     local_minima = get_local_minima(scores, grid_size)
 
     return optimize_local_minima_batched(local_minima, kappas, grid_size, batch)
+
+
+# ------------------------------------------------------------------------------------------------
+# many clips at once (BASELINE config 5): clips sharded over ranks, one all-gather of the scores
+# ------------------------------------------------------------------------------------------------
+
+
+class _ClipBank:
+    """The rank's clips resident on its GPU as one planar ``(n, 2, frames)`` float32 tensor, and the evaluation of
+    ragged (clip, strengths) requests on them: ONE tap program for all requested strengths, uploaded once, one
+    launch per clip on a sub-range of its candidates, one download of all partial sums, one vectorised scoring pass."""
+
+    def __init__(self, clips, family: Callable[[Sequence[float]], TapProgram], kw: dict):
+        import torch
+
+        if R.is_torch_tensor(clips):
+            if not clips.is_cuda or clips.dtype != torch.float32 or clips.dim() != 3 or clips.shape[1] != 2:
+                raise ValueError("clips must be a CUDA float32 tensor of shape (n_clips, 2, frames)")
+            self.clips = clips.contiguous()
+        else:
+            host = _planar_clips(clips)
+            self.clips = torch.from_numpy(host).to(f"cuda:{R.default_device()}")
+        self.n, _, self.frames = self.clips.shape
+        self.device = self.clips.device
+        self.family = family
+        self.kw = kw
+        self.evaluations = 0
+        self.launches = 0
+        self._work = None
+
+    def _workspace(self, n_cand: int):
+        import torch
+
+        nbytes = C.c_size_t()
+        N.check(N.lib().vnd_objective_workspace(self.frames, 1, n_cand, C.byref(nbytes)), "vnd_objective_workspace")
+        if self._work is None or self._work.numel() < nbytes.value:
+            self._work = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        return self._work, nbytes.value
+
+    def partials(self, requests: Sequence[Sequence[float]]):
+        """``requests[i]`` = strengths to evaluate on clip ``i``; returns the float64 partial sums
+        ``(total, OBJ_SLOTS)`` in request order (a CUDA tensor) and the per-clip counts."""
+        import torch
+
+        counts = [len(r) for r in requests]
+        total = sum(counts)
+        out = torch.empty((total, N.OBJ_SLOTS), dtype=torch.float64, device=self.device)
+        if total == 0:
+            return out, counts
+        flat = [float(k) for r in requests for k in r]
+        shared = len(set(counts)) == 1 and all(list(r) == list(requests[0]) for r in requests[1:])
+        lib = N.lib()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            if shared:  # the grid stage: every clip scores the same strengths -> one launch over clips x candidates
+                prog = self.family(flat[: counts[0]])
+                ps = R.device_program(prog, self.device)
+                nbytes = C.c_size_t()
+                N.check(lib.vnd_objective_workspace(self.frames, self.n, prog.channels, C.byref(nbytes)), "vnd_objective_workspace")
+                work = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+                N.check(lib.vnd_vn_objective_batch_dev(self.clips.data_ptr(), self.frames, self.n, 2 * self.frames, self.frames, C.byref(ps),
+                                                       out.data_ptr(), work.data_ptr(), nbytes.value, stream), "vnd_vn_objective_batch_dev")
+                self.launches += 1
+            else:
+                prog = self.family(flat)
+                ps = R.device_program(prog, self.device)
+                work, wbytes = self._workspace(max(counts))
+                base = 0
+                for i, n_i in enumerate(counts):
+                    if n_i == 0:
+                        continue
+                    sub = N.TapProgramStruct(ps.words, ps.offsets + 4 * base, ps.n_words, n_i, ps.order, ps.apply_gain, ps.halo, ps.max_channel_words)
+                    N.check(lib.vnd_vn_objective_batch_dev(self.clips.data_ptr() + 4 * i * 2 * self.frames, self.frames, 1, 2 * self.frames, self.frames,
+                                                           C.byref(sub), out.data_ptr() + 8 * N.OBJ_SLOTS * base, work.data_ptr(), wbytes, stream),
+                            "vnd_vn_objective_batch_dev")
+                    self.launches += 1
+                    base += n_i
+        self.evaluations += total
+        return out, counts
+
+    def scores(self, requests: Sequence[Sequence[float]]) -> list[np.ndarray]:
+        p, counts = self.partials(requests)
+        flat = vn_scores_from_partials(p.cpu().numpy(), **self.kw) if p.shape[0] else np.zeros(0, dtype=np.float32)
+        out, base = [], 0
+        for n_i in counts:
+            out.append(flat[base: base + n_i])
+            base += n_i
+        return out
+
+
+def optimize_velvet_noise_batch(*, input_signals, sample_rate_hz: int, duration_seconds: float, num_impulses: int, seed: int = 1,
+                                grid_size: int = 400, angle_limit: float = np.pi / 4, lambda_mean: float = 5.0, lambda_skew: float = 2.0,
+                                lambda_correlation: float = 15.0, lambda_penalty: float = 1e3, group=None, details: bool = False,
+                                _bank_factory=None):
+    """``optimize_velvet_noise`` (optimization.py:230-310) for MANY clips of equal length: returns the float64 array of
+    optimised ``log_distribution_strength`` values, element ``i`` equal to what ``optimize_velvet_noise(input_signal=
+    input_signals[i], ...)`` returns.
+
+    ``input_signals``: a sequence of ``(frames, 2)`` arrays, a planar ``(n_clips, 2, frames)`` float32 array, or a CUDA
+    tensor of that shape.  With ``torch.distributed`` initialised (one process per GPU) the clips are partitioned in
+    contiguous blocks over the ranks of ``group``; every rank must pass the SAME ``input_signals`` (only its block is
+    uploaded).  Data path per rank: grid scores of its clips (one launch over clips x grid) -> ONE all-gather of the
+    float32 score matrix so that every rank holds all rows (``get_local_minima`` needs both neighbours of every grid
+    point, optimization.py:120-128) -> lock-step Brent refinement of the local minima of its own clips -> one
+    all-gather of the refined strengths.  ``details=True`` also returns the score matrix, the local-minima sets and
+    evaluation counts."""
+    from . import sharding as S
+
+    kw = dict(angle_limit=angle_limit, lambda_mean=lambda_mean, lambda_skew=lambda_skew, lambda_correlation=lambda_correlation,
+              lambda_penalty=lambda_penalty)
+    n_clips = input_signals.shape[0] if (R.is_torch_tensor(input_signals) or (isinstance(input_signals, np.ndarray) and input_signals.ndim == 3)) \
+        else len(input_signals)
+    rank, world = S._world(group)
+    lo, hi = S.block_range(n_clips, rank, world)
+    local = input_signals[lo:hi]
+
+    def candidate(kappa):
+        return VelvetNoise(sample_rate_hz=sample_rate_hz, duration_seconds=duration_seconds, num_impulses=num_impulses,
+                           log_distribution_strength=kappa, normalizer=None, filtered_channels=(0,), mode="LR", seed=seed)
+
+    envelope = candidate(0.0).segment_envelope
+    frames_box: list[int] = []
+
+    def family(ks):
+        frames = frames_box[0]
+        prog = kappa_family_program(ks, sample_rate_hz=sample_rate_hz, duration_seconds=duration_seconds, num_impulses=num_impulses,
+                                    envelope=envelope, seed=seed, frames=frames) if seed is not None else None
+        return prog if prog is not None else _vn_family_program([candidate(k) for k in ks], frames)
+
+    kappas = np.linspace(0.0, 1.0, grid_size)
+    if hi > lo:
+        bank = (_bank_factory or _ClipBank)(local, family, kw)
+        frames_box.append(bank.frames)
+        print("Starting Grid Scan")
+        local_scores = np.stack(bank.scores([kappas] * (hi - lo))).astype(np.float32)
+    else:
+        bank = None
+        local_scores = np.zeros((0, grid_size), dtype=np.float32)
+
+    counts = [S.block_range(n_clips, r, world)[1] - S.block_range(n_clips, r, world)[0] for r in range(world)]
+    device = bank.device if (bank is not None and getattr(bank, "device", None) is not None) else S.collective_device(group)
+    scores = S.all_gather_rows(local_scores, counts, device=device, group=group)  # every rank: (n_clips, grid)
+
+    minima = [get_local_minima(row, grid_size) for row in scores]
+    best = np.zeros(hi - lo, dtype=np.float64)
+    if hi > lo:
+        print("Starting Local Minima optimization")
+        bounds, owner = [], []
+        for ci in range(lo, hi):
+            for i in minima[ci]:
+                bounds.append((kappas[max(0, i - 1)], kappas[min(grid_size - 1, i + 1)]))
+                owner.append(ci - lo)
+
+        def batch(xs, ids):
+            req: list[list[float]] = [[] for _ in range(hi - lo)]
+            for x, j in zip(xs, ids):
+                req[owner[j]].append(x)
+            vals = bank.scores(req)
+            pos = [0] * (hi - lo)
+            out = []
+            for j in ids:
+                c = owner[j]
+                out.append(vals[c][pos[c]])
+                pos[c] += 1
+            return out
+
+        results = lockstep_minimize(bounds, batch, xatol=1e-4, with_ids=True)
+        best_score = [np.inf] * (hi - lo)
+        for res, c in zip(results, owner):  # first strictly best minimum of each clip (optimization.py:150-153)
+            if res.fun < best_score[c]:
+                best_score[c] = res.fun
+                best[c] = res.x
+    refined = S.all_gather_rows(best.reshape(-1, 1), counts, device=device, group=group).reshape(-1)
+    if details:
+        info = {"scores": scores, "local_minima": minima, "argmin": [int(np.argmin(r)) for r in scores],
+                "evaluations_local": bank.evaluations if bank is not None else 0, "launches_local": bank.launches if bank is not None else 0,
+                "clips_local": (lo, hi)}
+        return refined, info
+    return refined

@@ -53,27 +53,41 @@ def _world(group=None) -> tuple[int, int]:
     return 0, 1
 
 
+def collective_device(group=None):
+    """Where a collective of ``group`` must run: the current CUDA device for NCCL, ``None`` (CPU) for gloo."""
+    dist = _dist()
+    if dist.is_available() and dist.is_initialized() and dist.get_backend(group) == "nccl":
+        import torch
+
+        return torch.device("cuda", torch.cuda.current_device())
+    return None
+
+
 def all_gather_rows(local_rows: np.ndarray, counts: Sequence[int], *, device=None, group=None) -> np.ndarray:
     """Concatenate per-rank row blocks (rank r contributes ``counts[r]`` rows) on every rank.
 
-    Uses one ``all_gather`` of equally sized (padded) tensors; ``device`` selects where the
-    collective runs (a CUDA device for NCCL, ``None``/cpu for gloo)."""
+    ONE collective on ONE tensor: the blocks are padded to the longest and gathered with
+    ``all_gather_into_tensor`` into a single ``(world * longest, ...)`` buffer (no list of per-rank tensors, one
+    device-to-host copy); ``device`` selects where it runs (a CUDA device for NCCL, ``None``/cpu for gloo)."""
     import torch
 
     dist = _dist()
     rank, world = _world(group)
     if world == 1:
         return np.ascontiguousarray(local_rows)
-    width = local_rows.shape[1:]
+    width = tuple(local_rows.shape[1:])
     longest = max(counts)
     pad = np.zeros((longest, *width), dtype=local_rows.dtype)
     pad[: local_rows.shape[0]] = local_rows
     t = torch.from_numpy(pad)
     if device is not None:
-        t = t.to(device)
-    out = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(out, t, group=group)
-    return np.concatenate([o.cpu().numpy()[: counts[r]] for r, o in enumerate(out)], axis=0)
+        t = t.to(device, non_blocking=True)
+    out = torch.empty((world * longest, *width), dtype=t.dtype, device=t.device)  # rank blocks concatenated along dim 0
+    dist.all_gather_into_tensor(out, t, group=group)
+    full = out.cpu().numpy()
+    if all(c == longest for c in counts):
+        return full
+    return np.concatenate([full[r * longest: r * longest + counts[r]] for r in range(world)], axis=0)
 
 
 def sweep_scores_sharded(

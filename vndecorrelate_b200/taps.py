@@ -40,6 +40,29 @@ def _interval_grid(strength: float, num_impulses: int, fir_length: int):
     return w, starts
 
 
+def _interval_grid_family(strengths, num_impulses: int, fir_length: int):
+    """``_interval_grid`` for many strengths at once: ``(K, N + 1)`` weights and interval starts.
+
+    The per-element operations and their order are those of ``_interval_grid`` (elementwise ``**`` and divisions, a
+    sequential ``cumsum`` per row), so the rows equal the one-strength results bit for bit; three rows are checked
+    against the one-strength function on every call and the loop is used if they ever differ (a numpy build whose
+    vector and scalar ``pow`` round differently).  ``tests/test_host_logic.py`` compares 20 000 strengths."""
+    ks = np.asarray(strengths, dtype=np.float64)
+    K = len(ks)
+    col = ks[:, None]
+    k = (np.arange(num_impulses + 1.0) / num_impulses)[None, :]
+    w = (10.0 ** (2.0 * col * k)) / (100.0 * ((1.0 + (col * 99.0)) / 100.0))
+    starts = np.cumsum(w, axis=1)
+    starts[ks == 0.0] -= 1.0
+    starts *= (fir_length / starts[:, -1])[:, None]
+    for i in {0, K // 2, K - 1}:
+        w1, s1 = _interval_grid(float(ks[i]), num_impulses, fir_length)
+        if not (np.array_equal(w1, w[i]) and np.array_equal(s1, starts[i])):
+            grids = [_interval_grid(float(v), num_impulses, fir_length) for v in ks]
+            return np.stack([g[0] for g in grids]), np.stack([g[1] for g in grids])
+    return w, starts
+
+
 def _segment_of_impulse(num_impulses: int, num_segments: int) -> np.ndarray:
     """``int(j / (N / S))`` with Python float division (decorrelation.py:540)."""
     return np.array([int(j / (num_impulses / num_segments)) for j in range(num_impulses)], dtype=np.int64)
@@ -385,9 +408,9 @@ def kappa_family_program(kappas, *, sample_rate_hz: int, duration_seconds: float
 
     With one seed every candidate draws the SAME uniforms (decorrelation.py:488, :510-521), so the signs, the
     decay segments and with them the order of the taps in a program are common to the family; only the interval
-    grid (``w``, ``starts``) depends on the strength.  The grid is still computed per candidate by the functions
-    the single-table path uses (same array shapes, hence the same numpy code paths and bits); positions, rounding
-    and packing are done for all candidates at once.  Returns None when the shortcut does not apply (a tap at or
+    grid (``w``, ``starts``) depends on the strength.  The grid comes from ``_interval_grid_family`` (the single-table
+    function's operations per element, verified against it); positions, rounding and packing are done for all
+    candidates at once.  Returns None when the shortcut does not apply (a tap at or
     beyond ``frames``, an empty decay segment, no impulses): the caller then packs table by table."""
     kappas = [float(k) for k in kappas]
     K = len(kappas)
@@ -398,9 +421,7 @@ def kappa_family_program(kappas, *, sample_rate_hz: int, duration_seconds: float
     fir_length = int(round(sample_rate_hz * duration_seconds))
     sign_u, offs_u = _draw(seed, num_impulses, 1)  # one filtered channel: channel 0
     jitter = sample_rate_hz / (num_impulses / duration_seconds)
-    grids = [_interval_grid(k, num_impulses, fir_length) for k in kappas]
-    w = np.stack([g[0] for g in grids])          # (K, N + 1)
-    starts = np.stack([g[1] for g in grids])     # (K, N + 1)
+    w, starts = _interval_grid_family(kappas, num_impulses, fir_length)  # (K, N + 1) each
     pos = np.round(offs_u[:, 0][None, :] * np.fmax(0.0, w * jitter - 1) + starts).astype(np.int32)[:, :num_impulses]
     positive = np.round(sign_u[:, 0]) == 1.0     # (N,)
     segment = _segment_of_impulse(num_impulses, S)
