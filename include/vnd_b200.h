@@ -12,8 +12,9 @@
  *   - "_dev" entry points take DEVICE pointers, an explicit cudaStream_t (passed as void*) and a
  *     caller-owned workspace: they never allocate, never synchronise, and are re-entrant on
  *     distinct streams.
- *   - "_host" entry points take HOST pointers and a vnd_ctx that owns a device arena, pinned
- *     staging and streams; host<->device copies happen inside the call.
+ *   - "_host" entry points take HOST pointers and a vnd_ctx that owns a device arena, page-locked
+ *     staging (used when the caller's buffers are pageable) and streams; host<->device copies happen
+ *     inside the call.
  *   - Signals are addressed as  element(t, c) = base[t * stride_t + c * stride_c]  (strides in
  *     ELEMENTS), so C-order (frames, channels) arrays (stride_t = C, stride_c = 1) and planar
  *     (channels, frames) arrays (stride_t = 1, stride_c = frames) use the same calls.
@@ -178,12 +179,20 @@ typedef struct vnd_ctx vnd_ctx;
 
 int vnd_ctx_create(int device, vnd_ctx** ctx);
 int vnd_ctx_destroy(vnd_ctx* ctx);
-/* Pinned host memory for callers that want zero-staging transfers. */
+/* Page-locked host memory for callers that want zero-staging transfers: buffers from these calls (or registered
+ * with cudaHostRegister) are copied by DMA directly; any other host buffer is staged through the context's own
+ * page-locked ring.  vnd_host_alloc allocates on the calling thread's current device, vnd_ctx_host_alloc on the
+ * context's device (it never touches another GPU). */
 int vnd_host_alloc(size_t bytes, void** ptr);
+int vnd_ctx_host_alloc(vnd_ctx* ctx, size_t bytes, void** ptr);
 int vnd_host_free(void* ptr);
 
 /* Host-buffer versions of the calls above (all pointers, including taps->words/offsets, are HOST
- * pointers).  Each call uploads, runs and downloads; on return the result is in `y`/`out`. */
+ * pointers).  Each call uploads, runs and downloads; on return the result is in `y`/`out`.
+ * vnd_sparse_fir_host overlaps the three for float32 slabs of 8 MB and more: planar (channels, frames) slabs are
+ * cut into channel groups, C-order (frames, channels) slabs - the reference's layout - into runs of frames
+ * uploaded with the filter's halo (wide ones are transposed to planar on the device around the kernel), and
+ * consecutive chunks flow through a three-deep device ring on three streams. */
 int vnd_sparse_fir_host(vnd_ctx* ctx, const vnd_signal* x, const vnd_signal* y, const vnd_tap_program* taps);
 int vnd_vn_decorrelate_host(vnd_ctx* ctx, const vnd_signal* x, const vnd_signal* out,
                             const vnd_tap_program* taps, const vnd_epilogue* ep);
@@ -197,11 +206,11 @@ int vnd_haas_objective_batch_host(vnd_ctx* ctx, const void* clips, int32_t clip_
                                   int64_t clip_stride, int64_t chan_stride, const int32_t* delays,
                                   int32_t n_cand, double* partials);
 
-/* Streaming planar FIR for slabs larger than one transfer: x and y are HOST planar
+/* The overlapped path of vnd_sparse_fir_host with an explicit stage size: x and y are HOST planar
  * (channels, frames) float32 slabs; channels are cut into groups of `channels_per_chunk`, and
- * upload / kernel / download of consecutive groups overlap on three streams.  Pinned buffers
- * (vnd_host_alloc) are copied directly; pageable ones go through the context's pinned staging.
- * This is the call bench.py's `e2e` figure times. */
+ * upload / kernel / download of consecutive groups overlap on three streams.  Page-locked buffers
+ * (vnd_host_alloc) are copied directly; pageable ones go through the context's page-locked staging ring,
+ * filled and drained by two helper threads. */
 int vnd_sparse_fir_stream_host(vnd_ctx* ctx, const float* x, float* y, int64_t frames, int32_t channels,
                                const vnd_tap_program* taps, int32_t channels_per_chunk);
 

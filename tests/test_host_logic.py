@@ -495,14 +495,26 @@ def test_pinned_output_pool_recycles_blocks(monkeypatch):
     libc.malloc.restype = C.c_void_p
     libc.malloc.argtypes = [C.c_size_t]
 
+    freed = []
+
     class FakeLib:
-        def vnd_host_alloc(self, nbytes, out):
+        def vnd_ctx_host_alloc(self, handle, nbytes, out):
             C.cast(out, C.POINTER(C.c_void_p))[0] = libc.malloc(nbytes)
             return 0
 
+        def vnd_host_free(self, ptr):
+            freed.append(ptr.value)
+            return 0
+
+    class FakeCtx:
+        handle = None
+
     monkeypatch.setattr(N, "lib", lambda: FakeLib())
+    monkeypatch.setattr(R.HostContext, "get", classmethod(lambda cls, device=None: FakeCtx()))
     monkeypatch.setattr(R, "_POOL_FREE", {})
     monkeypatch.setattr(R, "_POOL_BYTES", [0])
+    monkeypatch.setattr(R, "_POOL_CAP", [512 << 20])
+    monkeypatch.setattr(R, "_POOL_WARNED", [False])
     a = R.pinned_empty((1000, 2), np.float32)
     assert a.flags.writeable and not a.flags.owndata and R._POOL_BYTES[0] == 1 << 16
     a[:] = 1.5
@@ -516,6 +528,51 @@ def test_pinned_output_pool_recycles_blocks(monkeypatch):
     assert sum(len(v) for v in R._POOL_FREE.values()) == 1
     b = R.pinned_empty((500, 4), np.float32)  # same block size: recycled, no new allocation
     assert b.ctypes.data == ptr and R._POOL_BYTES[0] == 1 << 16
-    monkeypatch.setattr(R, "_POOL_CAP", 1 << 16)
-    c = R.pinned_empty((1 << 15,), np.float32)  # 128 KB more would exceed the cap: ordinary memory
-    assert c.flags.owndata
+    # at the cap: an idle block of another size class is released to make room ...
+    del b
+    gc.collect()
+    R.set_pinned_pool_cap(1 << 17)
+    c = R.pinned_empty((1 << 15,), np.float32)  # 128 KB: needs the 64 KB block gone
+    assert not c.flags.owndata and freed == [ptr] and R._POOL_BYTES[0] == 1 << 17
+    # ... and when nothing can be released the result is ordinary memory, with one warning
+    with pytest.warns(ResourceWarning):
+        d = R.pinned_empty((1000,), np.float32)
+    assert d.flags.owndata and R._POOL_BYTES[0] == 1 << 17
+    # a forked child forgets the parent's blocks instead of recycling their pointers
+    R._pinned_pool_after_fork()
+    assert R._POOL_FREE == {} and R._POOL_BYTES[0] == 0
+
+
+def test_random_tap_tables_match_reference():
+    """240 random (sample rate, duration, impulses, strength, seed, outputs, envelope) tuples: the class-path tap rows
+    and the dense FIR of the function path hash to what the UNMODIFIED reference produced
+    (tests/golden/make_golden_r02.py::random_tables)."""
+    import json
+    import os
+
+    recs = json.load(open(os.path.join(G.GOLDEN, "tables_random.json")))
+    assert len(recs) >= 200
+    for rec in recs:
+        p = rec["params"]
+        t = T.generate_tap_table(sample_rate_hz=p["sample_rate_hz"], duration_seconds=p["duration_seconds"], num_impulses=p["num_impulses"],
+                                 num_outs=p["num_outs"], num_segments=len(p["segment_envelope"]), log_distribution_strength=p["log_distribution_strength"],
+                                 filtered_channels=tuple(p["filtered_channels"]), seed=p["seed"])
+        rows = t.rows()
+        assert rows.shape[0] == rec["class_rows_count"] and G.sha(rows) == rec["class_rows_sha256"], p
+        fir = T.generate_dense_fir(duration_seconds=p["duration_seconds"], num_impulses=p["num_impulses"], num_outs=p["num_outs"],
+                                   sample_rate_hz=p["sample_rate_hz"], segment_envelope=tuple(p["segment_envelope"]),
+                                   log_distribution_strength=p["log_distribution_strength"], seed=p["seed"])
+        assert list(fir.shape) == rec["dense_shape"] and G.sha(fir) == rec["dense_sha256"], p
+
+
+def test_interval_grid_family_is_bitwise_the_single_strength_grid():
+    """taps._interval_grid_family (one vectorised pass for all strengths of a sweep or of a Brent round) against the
+    single-strength function, 20 000 strengths incl. the end points and Brent-like values."""
+    rng = np.random.default_rng(3)
+    ks = np.concatenate([np.linspace(0.0, 1.0, 1024), rng.uniform(0.0, 1.0, 20000), [0.0, 1.0, 1e-300, 0.5, 0.3201472263050255]])
+    for n_imp, fir_len in ((30, 1440), (15, 1323), (300, 28800)):
+        sub = ks if n_imp == 30 else ks[:3000]
+        w, s = T._interval_grid_family(sub, n_imp, fir_len)
+        for i in range(0, len(sub), 7):
+            w1, s1 = T._interval_grid(float(sub[i]), n_imp, fir_len)
+            assert np.array_equal(w1, w[i]) and np.array_equal(s1, s[i])

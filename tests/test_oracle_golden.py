@@ -274,3 +274,22 @@ def test_optimisers_short_excerpt():
     ref = G.objective()["optimize_haas_viola_40k"]
     t, _, _ = O.optimize_haas(sig, sample_rate_hz=fs, max_delay_seconds=0.03, grid_size=ref["grid_size"])
     assert abs(t - ref["tau"]) <= 1e-9
+
+
+def test_oracle_random_tap_tables_match_reference():
+    """The oracle's tap generation against the 240 random tuples hashed from the reference
+    (tests/golden/make_golden_r02.py::random_tables)."""
+    import json
+    import os
+
+    recs = json.load(open(os.path.join(G.GOLDEN, "tables_random.json")))
+    for rec in recs[::3]:  # the pure-Python loops of the oracle are slow: every third tuple
+        p = rec["params"]
+        taps = O.class_taps(sample_rate_hz=p["sample_rate_hz"], duration_seconds=p["duration_seconds"], num_impulses=p["num_impulses"],
+                            num_outs=p["num_outs"], num_segments=len(p["segment_envelope"]), log_distribution_strength=p["log_distribution_strength"],
+                            filtered_channels=tuple(p["filtered_channels"]), seed=p["seed"])
+        assert G.sha(O.table_rows(taps)) == rec["class_rows_sha256"], p
+        fir = O.dense_fir(duration_seconds=p["duration_seconds"], num_impulses=p["num_impulses"], num_outs=p["num_outs"],
+                          sample_rate_hz=p["sample_rate_hz"], segment_envelope=tuple(p["segment_envelope"]),
+                          log_distribution_strength=p["log_distribution_strength"], seed=p["seed"])
+        assert G.sha(fir) == rec["dense_sha256"], p

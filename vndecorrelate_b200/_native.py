@@ -85,6 +85,7 @@ SIGNATURES = {
     "vnd_ctx_create": (C.c_int, [C.c_int, _P(C.c_void_p)]),
     "vnd_ctx_destroy": (C.c_int, [C.c_void_p]),
     "vnd_host_alloc": (C.c_int, [C.c_size_t, _P(C.c_void_p)]),
+    "vnd_ctx_host_alloc": (C.c_int, [C.c_void_p, C.c_size_t, _P(C.c_void_p)]),
     "vnd_host_free": (C.c_int, [C.c_void_p]),
     "vnd_sparse_fir_host": (C.c_int, [C.c_void_p, _P(SignalStruct), _P(SignalStruct), _P(TapProgramStruct)]),
     "vnd_vn_decorrelate_host": (C.c_int, [C.c_void_p, _P(SignalStruct), _P(SignalStruct), _P(TapProgramStruct), _P(EpilogueStruct)]),

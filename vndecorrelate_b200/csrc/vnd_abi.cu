@@ -2,10 +2,14 @@
 // entry points, and the host-buffer entry points with their context (device arena, streams,
 // pinned staging).
 
+#include <cuda.h>  // CUcontext / CUresult types only: cuCtxGetCurrent is fetched through cudaGetDriverEntryPoint
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "vnd_common.cuh"
@@ -25,6 +29,7 @@ int haas_launch(const vnd_signal* x, const vnd_signal* out, int delay, int delay
                 double width, cudaStream_t st);
 int stereo_op_launch(const vnd_signal* a, const vnd_signal* dry, int op, double width, const void* gains, cudaStream_t st);
 int transpose_launch(const float* src, float* dst, long long rows, long long cols, cudaStream_t st);
+int transpose_launch_ld(const float* src, float* dst, long long rows, long long cols, long long ld_src, long long ld_dst, cudaStream_t st);
 int objective_workspace_bytes(long long frames, int n_clips, int n_cand, size_t* bytes);
 int vn_objective_launch(const float* clips, long long frames, int n_clips, long long clip_stride, long long chan_stride,
                         const vnd_tap_program* cand, double* partials, void* workspace, size_t workspace_bytes, cudaStream_t st);
@@ -271,13 +276,14 @@ struct vnd_ctx {
     void* p = nullptr;
     size_t cap = 0;
   };
-  Buf slots[12];  // grow-only device arena
+  Buf slots[18];  // grow-only device arena
+  Buf pin[4];     // grow-only page-locked staging for pageable callers: [0,1] upload ring, [2,3] download ring
   std::mutex mu;
 };
 
 namespace {
 
-enum Slot { S_IN = 0, S_OUT = 1, S_WORK = 2, S_WORDS = 3, S_OFFS = 4, S_AUX = 5, S_RING = 6 /* 6..11 */ };
+enum Slot { S_IN = 0, S_OUT = 1, S_WORK = 2, S_WORDS = 3, S_OFFS = 4, S_AUX = 5, S_RING = 6 /* 6..11 */, S_SCRATCH = 12 /* 12..17 */ };
 
 int arena(vnd_ctx* ctx, int slot, size_t bytes, void** out) {
   vnd_ctx::Buf& b = ctx->slots[slot];
@@ -330,12 +336,34 @@ int upload_program(vnd_ctx* ctx, const vnd_tap_program* host, vnd_tap_program* d
   return VND_OK;
 }
 
+// Does the calling thread have a CUDA context bound?  (cudaGetDevice answers 0 either way, and since CUDA 12
+// cudaSetDevice CREATES the primary context of the device it names.)
+bool thread_has_context() {
+  typedef CUresult (*GetCurrentFn)(CUcontext*);
+  static GetCurrentFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    (void)cudaGetLastError();
+    return reinterpret_cast<GetCurrentFn>(p);
+  }();
+  if (!fn) return true;  // cannot tell: behave like a plain save / restore
+  CUcontext c = nullptr;
+  return fn(&c) == CUDA_SUCCESS && c != nullptr;
+}
+
+// Selects the context's device for the duration of a call.  The previous device is restored only if the thread
+// HAD a context before: restoring "device 0" for a thread that never touched CUDA would create a primary context
+// (about half a GB) on GPU 0 in every rank of a multi-GPU job, and fails under exclusive-process compute mode.
 struct DeviceGuard {
   int prev = -1;
   bool ok = true;
   explicit DeviceGuard(int dev) {
-    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-    ok = cudaSetDevice(dev) == cudaSuccess;
+    if (thread_has_context()) {
+      if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    }
+    ok = (prev == dev) || cudaSetDevice(dev) == cudaSuccess;
+    if (prev == dev) prev = -1;
   }
   ~DeviceGuard() {
     if (prev >= 0) cudaSetDevice(prev);
@@ -386,6 +414,8 @@ extern "C" int vnd_ctx_destroy(vnd_ctx* ctx) {
       }
     for (auto& b : ctx->slots)
       if (b.p) cudaFree(b.p);
+    for (auto& b : ctx->pin)
+      if (b.p) cudaFreeHost(b.p);
   }
   delete ctx;
   return VND_OK;
@@ -398,10 +428,300 @@ extern "C" int vnd_host_alloc(size_t bytes, void** ptr) {
   return VND_OK;
 }
 
+extern "C" int vnd_ctx_host_alloc(vnd_ctx* ctx, size_t bytes, void** ptr) {
+  VND_REQUIRE(ctx != nullptr, VND_EINVAL, "context is null");
+  VND_REQUIRE(ptr != nullptr, VND_EINVAL, "ptr is null");
+  *ptr = nullptr;
+  DeviceGuard guard(ctx->device);
+  VND_REQUIRE(guard.ok, VND_ECUDA, "cudaSetDevice(%d) failed", ctx->device);
+  VND_CUDA_OK(cudaHostAlloc(ptr, bytes ? bytes : 16, cudaHostAllocPortable));
+  return VND_OK;
+}
+
 extern "C" int vnd_host_free(void* ptr) {
   if (ptr) VND_CUDA_OK(cudaFreeHost(ptr));
   return VND_OK;
 }
+
+// ================================================================================================
+// overlapped host path: upload / kernels / download of consecutive chunks on three streams
+// ================================================================================================
+namespace {
+
+int staging(vnd_ctx* ctx, int slot, size_t bytes, void** out) {
+  vnd_ctx::Buf& b = ctx->pin[slot];
+  if (b.cap < bytes) {
+    if (b.p) VND_CUDA_OK(cudaFreeHost(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    cudaError_t e = cudaHostAlloc(&b.p, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("pinned staging: cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+      return VND_ENOMEM;
+    }
+    b.cap = bytes;
+  }
+  *out = b.p;
+  return VND_OK;
+}
+
+// Page-locked (cudaHostAlloc / cudaHostRegister) memory is copied by DMA straight from / to the caller's
+// buffer; anything else goes through the context's staging ring.
+bool is_page_locked(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+struct PipeChunk {
+  const char* src;   // host bytes uploaded for this chunk (contiguous)
+  size_t src_bytes;
+  char* dst;         // host bytes this chunk produces (contiguous)
+  size_t dst_bytes;
+};
+
+struct PipeSync {
+  std::mutex mu;
+  std::condition_variable cv;
+  long long staged = -1, h2d_enqueued = -1, d2h_enqueued = -1, copied = -1;
+  bool abort = false;
+  void set(long long PipeSync::*field, long long v) {
+    {
+      std::lock_guard<std::mutex> l(mu);
+      this->*field = v;
+    }
+    cv.notify_all();
+  }
+  bool wait(long long PipeSync::*field, long long v) {  // false when the pipeline was aborted
+    std::unique_lock<std::mutex> l(mu);
+    cv.wait(l, [&] { return abort || this->*field >= v; });
+    return !abort;
+  }
+  void stop() {
+    {
+      std::lock_guard<std::mutex> l(mu);
+      abort = true;
+    }
+    cv.notify_all();
+  }
+};
+
+constexpr int kPipeSlots = 3;
+
+// Runs n chunks through a ring of kPipeSlots device buffers: ctx->streams[0] uploads, [1] computes, [2] downloads,
+// ordered by events, so the upload of chunk k + 1 and the download of chunk k - 1 overlap the kernels of chunk k
+// (PCIe is full duplex).  `compute(k, din, dout, scratch_a, scratch_b, stream)` enqueues the kernels of chunk k.
+// Pageable host buffers are staged through the context's page-locked ring by two helper threads (one copies
+// chunks in ahead of the uploads, one copies finished chunks out), so the caller's thread only enqueues.
+template <class ChunkOf, class Compute>
+int run_pipeline(vnd_ctx* ctx, int n, size_t in_cap, size_t out_cap, size_t scratch_cap, ChunkOf chunk_of, Compute compute) {
+  if (n <= 0) return VND_OK;
+  int rc;
+  cudaStream_t up = ctx->streams[0], comp = ctx->streams[1], down = ctx->streams[2];
+  void *din[kPipeSlots], *dout[kPipeSlots], *sa[kPipeSlots], *sb[kPipeSlots];
+  for (int s = 0; s < kPipeSlots; ++s) {
+    if ((rc = arena(ctx, S_RING + 2 * s, in_cap, &din[s]))) return rc;
+    if ((rc = arena(ctx, S_RING + 2 * s + 1, out_cap, &dout[s]))) return rc;
+    sa[s] = sb[s] = nullptr;
+    if (scratch_cap) {
+      if ((rc = arena(ctx, S_SCRATCH + 2 * s, scratch_cap, &sa[s]))) return rc;
+      if ((rc = arena(ctx, S_SCRATCH + 2 * s + 1, scratch_cap, &sb[s]))) return rc;
+    }
+  }
+  const PipeChunk first = chunk_of(0);
+  const bool in_locked = is_page_locked(first.src), out_locked = is_page_locked(first.dst);
+  void *pin_in[2] = {nullptr, nullptr}, *pin_out[2] = {nullptr, nullptr};
+  if (!in_locked)
+    for (int i = 0; i < 2; ++i)
+      if ((rc = staging(ctx, i, in_cap, &pin_in[i]))) return rc;
+  if (!out_locked)
+    for (int i = 0; i < 2; ++i)
+      if ((rc = staging(ctx, 2 + i, out_cap, &pin_out[i]))) return rc;
+
+  std::vector<cudaEvent_t> ev(3 * (size_t)n, nullptr);
+  auto ev_up = [&](int k) -> cudaEvent_t& { return ev[3 * (size_t)k]; };
+  auto ev_comp = [&](int k) -> cudaEvent_t& { return ev[3 * (size_t)k + 1]; };
+  auto ev_down = [&](int k) -> cudaEvent_t& { return ev[3 * (size_t)k + 2]; };
+  rc = VND_OK;
+  for (auto& e : ev)
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+      set_error("cudaEventCreate failed");
+      rc = VND_ECUDA;
+      break;
+    }
+
+  PipeSync sync;
+  std::thread stage_in, stage_out;
+  const int device = ctx->device;
+  if (rc == VND_OK && !in_locked)
+    stage_in = std::thread([&] {  // copies chunk k into staging slot k % 2 once the upload of chunk k - 2 has left it
+      cudaSetDevice(device);
+      for (int k = 0; k < n; ++k) {
+        if (k >= 2) {
+          if (!sync.wait(&PipeSync::h2d_enqueued, k - 2)) return;
+          if (cudaEventSynchronize(ev_up(k - 2)) != cudaSuccess) return sync.stop();
+        }
+        const PipeChunk c = chunk_of(k);
+        memcpy(pin_in[k & 1], c.src, c.src_bytes);
+        sync.set(&PipeSync::staged, k);
+      }
+    });
+  if (rc == VND_OK && !out_locked)
+    stage_out = std::thread([&] {  // copies finished chunk k out of staging slot k % 2
+      cudaSetDevice(device);
+      for (int k = 0; k < n; ++k) {
+        if (!sync.wait(&PipeSync::d2h_enqueued, k)) return;
+        if (cudaEventSynchronize(ev_down(k)) != cudaSuccess) return sync.stop();
+        const PipeChunk c = chunk_of(k);
+        memcpy(c.dst, pin_out[k & 1], c.dst_bytes);
+        sync.set(&PipeSync::copied, k);
+      }
+    });
+
+#define VND_PIPE_OK(expr)                                                                           \
+  if (rc == VND_OK) {                                                                               \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);        \
+      rc = VND_ECUDA;                                                                               \
+    }                                                                                               \
+  }
+  for (int k = 0; k < n && rc == VND_OK; ++k) {
+    const int s = k % kPipeSlots;
+    const PipeChunk c = chunk_of(k);
+    // upload (the slot's input buffer is free once the kernels of chunk k - slots have run)
+    if (k >= kPipeSlots) VND_PIPE_OK(cudaStreamWaitEvent(up, ev_comp(k - kPipeSlots), 0));
+    if (!in_locked && !sync.wait(&PipeSync::staged, k)) {
+      set_error("pipeline staging failed");
+      rc = VND_ECUDA;
+      break;
+    }
+    VND_PIPE_OK(cudaMemcpyAsync(din[s], in_locked ? (const void*)c.src : pin_in[k & 1], c.src_bytes, cudaMemcpyHostToDevice, up));
+    VND_PIPE_OK(cudaEventRecord(ev_up(k), up));
+    if (!in_locked) sync.set(&PipeSync::h2d_enqueued, k);
+    // kernels (the slot's output buffer is free once chunk k - slots has been downloaded)
+    VND_PIPE_OK(cudaStreamWaitEvent(comp, ev_up(k), 0));
+    if (k >= kPipeSlots) VND_PIPE_OK(cudaStreamWaitEvent(comp, ev_down(k - kPipeSlots), 0));
+    if (rc == VND_OK) rc = compute(k, din[s], dout[s], sa[s], sb[s], comp);
+    VND_PIPE_OK(cudaEventRecord(ev_comp(k), comp));
+    // download
+    VND_PIPE_OK(cudaStreamWaitEvent(down, ev_comp(k), 0));
+    if (!out_locked && k >= 2 && !sync.wait(&PipeSync::copied, k - 2)) {
+      set_error("pipeline staging failed");
+      rc = VND_ECUDA;
+      break;
+    }
+    VND_PIPE_OK(cudaMemcpyAsync(out_locked ? (void*)c.dst : pin_out[k & 1], dout[s], c.dst_bytes, cudaMemcpyDeviceToHost, down));
+    VND_PIPE_OK(cudaEventRecord(ev_down(k), down));
+    if (!out_locked && rc == VND_OK) sync.set(&PipeSync::d2h_enqueued, k);
+  }
+  if (rc != VND_OK) sync.stop();
+  if (stage_in.joinable()) stage_in.join();
+  if (stage_out.joinable()) stage_out.join();
+  for (auto& st : ctx->streams) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess && rc == VND_OK) {
+      set_error("cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
+      rc = VND_ECUDA;
+    }
+  }
+  if (rc == VND_OK && sync.abort) {
+    set_error("pipeline staging thread failed");
+    rc = VND_ECUDA;
+  }
+  for (auto& e : ev)
+    if (e) cudaEventDestroy(e);
+#undef VND_PIPE_OK
+  return rc;
+}
+
+size_t pipe_chunk_bytes() {  // bytes uploaded per pipeline stage (VND_PIPE_CHUNK_MB, default 64)
+  const char* e = getenv("VND_PIPE_CHUNK_MB");
+  const long mb = e ? atol(e) : 64;
+  return (size_t)(mb > 0 ? mb : 64) << 20;
+}
+constexpr size_t kPipeMinBytes = 8u << 20;  // below this one blocking copy each way is as fast
+
+// Planar (channels, frames) float32 host slabs: chunks are groups of whole channels.
+int fir_pipeline_planar(vnd_ctx* ctx, const float* x, float* y, long long frames, int channels, const vnd_tap_program* dprog,
+                        int channels_per_chunk) {
+  if (channels_per_chunk <= 0) {
+    long long cpc = (long long)(pipe_chunk_bytes() / ((size_t)frames * 4));
+    if (cpc > (channels + 3) / 4) cpc = (channels + 3) / 4;  // at least four stages when there are four channels
+    channels_per_chunk = (int)(cpc < 1 ? 1 : cpc);
+  }
+  if (channels_per_chunk > channels) channels_per_chunk = channels;
+  const int n = (channels + channels_per_chunk - 1) / channels_per_chunk;
+  const size_t cap = (size_t)channels_per_chunk * frames * 4;
+  auto chunk_of = [&](int k) {
+    const int c0 = k * channels_per_chunk;
+    const int nc = channels - c0 < channels_per_chunk ? channels - c0 : channels_per_chunk;
+    const size_t bytes = (size_t)nc * frames * 4;
+    return PipeChunk{reinterpret_cast<const char*>(x + (size_t)c0 * frames), bytes, reinterpret_cast<char*>(y + (size_t)c0 * frames), bytes};
+  };
+  auto compute = [&](int k, void* din, void* dout, void*, void*, cudaStream_t st) {
+    const int c0 = k * channels_per_chunk;
+    const int nc = channels - c0 < channels_per_chunk ? channels - c0 : channels_per_chunk;
+    vnd_signal xd{din, frames, nc, VND_F32, 1, frames};
+    vnd_signal yd{dout, frames, nc, VND_F32, 1, frames};
+    vnd_tap_program sub = *dprog;
+    sub.channels = nc;
+    sub.offsets = dprog->offsets + c0;
+    return vnd_sparse_fir_dev(&xd, &yd, &sub, st);
+  };
+  return run_pipeline(ctx, n, cap, cap, 0, chunk_of, compute);
+}
+
+// C-order (frames, channels) float32 host slabs - the reference's layout: chunks are runs of frames (all channels,
+// contiguous on the host) uploaded with the filter's halo behind them; wide chunks are transposed to planar on the
+// device around the planar kernel, so that tiles load and store coalesced.
+int fir_pipeline_interleaved(vnd_ctx* ctx, const float* x, int x_channels, float* y, long long frames, int channels,
+                             const vnd_tap_program* dprog) {
+  long long halo = dprog->halo > 0 ? dprog->halo : 0;
+  halo = (halo + 3) & ~3LL;
+  long long T = (long long)(pipe_chunk_bytes() / ((size_t)x_channels * 4));
+  if (T > (frames + 3) / 4) T = (frames + 3) / 4;
+  if (T < 4 * halo) T = 4 * halo;  // the halo is uploaded twice: keep that below a quarter
+  T = (T + 3) & ~3LL;
+  if (T < 4) T = 4;
+  const int n = (int)((frames + T - 1) / T);
+  const bool wide = channels > 2 && x_channels == channels;
+  const size_t in_cap = (size_t)(T + halo) * x_channels * 4, out_cap = (size_t)(T + halo) * channels * 4;
+  auto span_of = [&](int k, long long* t0, long long* nt, long long* nin) {
+    *t0 = (long long)k * T;
+    *nt = frames - *t0 < T ? frames - *t0 : T;
+    *nin = frames - *t0 < T + halo ? frames - *t0 : T + halo;  // frames uploaded: the chunk and its halo, clipped at the end
+  };
+  auto chunk_of = [&](int k) {
+    long long t0, nt, nin;
+    span_of(k, &t0, &nt, &nin);
+    return PipeChunk{reinterpret_cast<const char*>(x + (size_t)t0 * x_channels), (size_t)nin * x_channels * 4,
+                     reinterpret_cast<char*>(y + (size_t)t0 * channels), (size_t)nt * channels * 4};
+  };
+  auto compute = [&](int k, void* din, void* dout, void* sa, void* sb, cudaStream_t st) {
+    long long t0, nt, nin;
+    span_of(k, &t0, &nt, &nin);
+    int rc;
+    if (wide) {
+      const long long ld = (nin + 3) & ~3LL;  // planar channel pitch: a multiple of 4 keeps the bulk-copy path
+      if ((rc = transpose_launch_ld((const float*)din, (float*)sa, nin, channels, channels, ld, st))) return rc;
+      vnd_signal xp{sa, nin, channels, VND_F32, 1, ld};
+      vnd_signal yp{sb, nin, channels, VND_F32, 1, ld};
+      if ((rc = vnd_sparse_fir_dev(&xp, &yp, dprog, st))) return rc;
+      return transpose_launch_ld((const float*)sb, (float*)dout, channels, nt, ld, channels, st);
+    }
+    vnd_signal xd{din, nin, x_channels, VND_F32, x_channels, 1};
+    vnd_signal yd{dout, nin, channels, VND_F32, channels, 1};
+    return vnd_sparse_fir_dev(&xd, &yd, dprog, st);
+  };
+  return run_pipeline(ctx, n, in_cap, out_cap, wide ? (size_t)(T + halo + 4) * channels * 4 : 0, chunk_of, compute);
+}
+
+}  // namespace
 
 extern "C" int vnd_sparse_fir_host(vnd_ctx* ctx, const vnd_signal* x, const vnd_signal* y, const vnd_tap_program* taps) {
   VND_ENTER(ctx);
@@ -412,6 +732,19 @@ extern "C" int vnd_sparse_fir_host(vnd_ctx* ctx, const vnd_signal* x, const vnd_
   cudaStream_t st = ctx->streams[0];
   vnd_tap_program dprog;
   if ((rc = upload_program(ctx, taps, &dprog, st))) return rc;
+  // Large float32 slabs: upload, kernels and download overlapped chunk by chunk (run_pipeline)
+  if (x->dtype == VND_F32 && y->dtype == VND_F32 && x->frames == y->frames && dx.elems * 4 >= kPipeMinBytes && x->stride_c != 0 &&
+      taps->channels == y->channels && x->channels >= y->channels && getenv("VND_NO_PIPELINE") == nullptr) {
+    const long long L = x->frames;
+    const int C = y->channels;
+    const bool x_planar = x->stride_t == 1 && (x->stride_c == L || x->channels == 1), y_planar = y->stride_t == 1 && (y->stride_c == L || C == 1);
+    const bool x_inter = x->stride_c == 1 && x->stride_t == x->channels, y_inter = y->stride_c == 1 && y->stride_t == C;
+    VND_CUDA_OK(cudaStreamSynchronize(st));  // the program is on the device before the other streams read it
+    if (x_planar && y_planar && x->channels == C && C > 1)
+      return fir_pipeline_planar(ctx, (const float*)x->data, (float*)y->data, L, C, &dprog, 0);
+    if (x_inter && y_inter && L >= 16LL * (taps->halo > 0 ? taps->halo : 1))
+      return fir_pipeline_interleaved(ctx, (const float*)x->data, x->channels, (float*)y->data, L, C, &dprog);
+  }
   void *din = nullptr, *dout = nullptr;
   if ((rc = arena(ctx, S_IN, dx.elems * esize(x->dtype), &din))) return rc;
   if ((rc = arena(ctx, S_OUT, dy.elems * 4, &dout))) return rc;
@@ -523,6 +856,7 @@ extern "C" int vnd_vn_objective_batch_host(vnd_ctx* ctx, const float* clips, int
   if ((rc = check_taps(cand))) return rc;
   VND_REQUIRE(frames >= 0 && n_clips >= 0, VND_EINVAL, "negative extent");
   if (n_clips == 0 || cand->channels == 0) return VND_OK;
+  VND_REQUIRE(frames > 0, VND_EINVAL, "objective of an empty signal (zero-size array to reduction operation maximum which has no identity)");
   VND_REQUIRE(clips != nullptr && partials != nullptr, VND_EINVAL, "null buffer");
   VND_REQUIRE(chan_stride >= frames && clip_stride >= chan_stride + frames, VND_EUNSUPPORTED, "clips must be planar: clip, channel, frame");
   cudaStream_t st = ctx->streams[0];
@@ -569,9 +903,9 @@ extern "C" int vnd_haas_objective_batch_host(vnd_ctx* ctx, const void* clips, in
   return VND_OK;
 }
 
-// Streaming planar FIR: channel groups flow through a 3-deep ring of (in, out) device buffers, one
-// stream per ring slot, so the upload of group g+1 and the download of group g-1 overlap the
-// kernel of group g (PCIe is full duplex).
+// Streaming planar FIR with an explicit stage size: channel groups flow through the 3-deep ring of run_pipeline
+// (upload, kernels and download on three streams; pageable buffers staged through page-locked memory by helper
+// threads).  vnd_sparse_fir_host takes the same path for any large float32 slab, planar or (frames, channels).
 extern "C" int vnd_sparse_fir_stream_host(vnd_ctx* ctx, const float* x, float* y, int64_t frames, int32_t channels,
                                           const vnd_tap_program* taps, int32_t channels_per_chunk) {
   VND_ENTER(ctx);
@@ -581,32 +915,8 @@ extern "C" int vnd_sparse_fir_stream_host(vnd_ctx* ctx, const float* x, float* y
   VND_REQUIRE(taps->channels == channels, VND_EINVAL, "tap program has %d channels, slab has %d", taps->channels, channels);
   if (frames == 0 || channels == 0) return VND_OK;
   VND_REQUIRE(x != nullptr && y != nullptr, VND_EINVAL, "null slab");
-  if (channels_per_chunk <= 0) channels_per_chunk = 1;
-  if (channels_per_chunk > channels) channels_per_chunk = channels;
   vnd_tap_program dprog;
   if ((rc = upload_program(ctx, taps, &dprog, ctx->streams[0]))) return rc;
   VND_CUDA_OK(cudaStreamSynchronize(ctx->streams[0]));
-  const size_t chunk_bytes = (size_t)channels_per_chunk * frames * 4;
-  void *din[3], *dout[3];
-  for (int s = 0; s < 3; ++s) {
-    if ((rc = arena(ctx, S_RING + 2 * s, chunk_bytes, &din[s]))) return rc;
-    if ((rc = arena(ctx, S_RING + 2 * s + 1, chunk_bytes, &dout[s]))) return rc;
-  }
-  int g = 0;
-  for (int c0 = 0; c0 < channels; c0 += channels_per_chunk, ++g) {
-    const int nc = channels - c0 < channels_per_chunk ? channels - c0 : channels_per_chunk;
-    const int s = g % 3;
-    cudaStream_t st = ctx->streams[s];
-    const size_t bytes = (size_t)nc * frames * 4;
-    VND_CUDA_OK(cudaMemcpyAsync(din[s], x + (size_t)c0 * frames, bytes, cudaMemcpyHostToDevice, st));
-    vnd_signal xd{din[s], frames, nc, VND_F32, 1, frames};
-    vnd_signal yd{dout[s], frames, nc, VND_F32, 1, frames};
-    vnd_tap_program sub = dprog;
-    sub.channels = nc;
-    sub.offsets = dprog.offsets + c0;
-    if ((rc = vnd_sparse_fir_dev(&xd, &yd, &sub, st))) return rc;
-    VND_CUDA_OK(cudaMemcpyAsync(y + (size_t)c0 * frames, dout[s], bytes, cudaMemcpyDeviceToHost, st));
-  }
-  for (auto& st : ctx->streams) VND_CUDA_OK(cudaStreamSynchronize(st));
-  return VND_OK;
+  return fir_pipeline_planar(ctx, x, y, frames, channels, &dprog, channels_per_chunk <= 0 ? 1 : channels_per_chunk);
 }

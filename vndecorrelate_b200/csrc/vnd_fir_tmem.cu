@@ -369,22 +369,26 @@ __device__ __forceinline__ void tap_list(const int* __restrict__ ops, int n, int
     // latency runs under the adds of tap k.  tcgen05.wait::ld waits for every outstanding load of the thread, hence
     // exactly one load is in flight at each wait.
     if (nn > 0) {
+      // One tap per half, with the loop exit BETWEEN the halves: the branch keeps ptxas from hoisting the adds of the
+      // buffer whose load was just issued above the adds of the buffer that has landed (it interleaves them when both
+      // sit in one basic block, and the warp then stalls on the fresh load with most of its adds still to issue).
       float ta[RG], tb[RG];
       near_issue(ta, tcol0 + (uint32_t)op_a);
-      for (; k + 1 < nn; k += 2) {
-        const int op_b = ops[k + 1];
-        const int op_c = ops[k + 2];  // slack words follow the lists
-        tmem_wait_ld(ta);
-        near_issue(tb, tcol0 + (uint32_t)op_b);
-        near_add<SUB>(ta, acc);
-        tmem_wait_ld(tb);
-        if (k + 2 < nn) near_issue(ta, tcol0 + (uint32_t)op_c);
-        near_add<SUB>(tb, acc);
-      }
-      if (k < nn) {
-        tmem_wait_ld(ta);
-        near_add<SUB>(ta, acc);
-        ++k;
+      for (;;) {
+        {
+          const int op_n = ops[k + 1];  // slack words follow the lists
+          tmem_wait_ld(ta);
+          if (k + 1 < nn) near_issue(tb, tcol0 + (uint32_t)op_n);
+          near_add<SUB>(ta, acc);
+          if (++k >= nn) break;
+        }
+        {
+          const int op_n = ops[k + 1];
+          tmem_wait_ld(tb);
+          if (k + 1 < nn) near_issue(ta, tcol0 + (uint32_t)op_n);
+          near_add<SUB>(tb, acc);
+          if (++k >= nn) break;
+        }
       }
       if (k >= n) return;
       op_a = ops[k];
@@ -467,7 +471,7 @@ extern __shared__ __align__(128) unsigned char tm_smem[];
 template <class T>
 struct Smem {
   uint64_t* bars;
-  int* s_near_end;  // [G]
+  int* s_near_end;  // first segment without a tap in every group's TMEM window
   float* in_all;
   float* stage;
   int* sprog;
@@ -523,30 +527,48 @@ __device__ __forceinline__ bool begin_run(const TmParams& P, const Smem<T>& sm, 
   const int S = sm.sprog[0];
   const int* taps = sm.sprog + 1 + 3 * S;
   const int ntaps = r.nprog - 1 - 3 * S;
-  if (tid < T::kG) {  // per thread group: the segment table; segments from near_end on have no tap inside the group's TMEM reach
-    const int g = tid, nmax = T::near_max(g);
-    int4* st = sm.segtab + g * (sm.opstride / 2);
+  // Segments from near_end on have no tap inside the TMEM window of EVERY group (offsets <= 512 - R): the compute
+  // warps release the quarter's TMEM for the next tile's refill when they reach it, and the refill then runs under
+  // their trailing all-far segments.  Inside the earlier segments a group may serve more taps from TMEM than that:
+  // group g's columns start RG g into the row, so its reach is 512 - RG (g + 1).  (Letting a group keep TMEM taps
+  // in the trailing segments would hold the refill back for the whole quarter.)
+  if (tid == 0) {
     const int* tq = taps;
     int ne = 0;
     for (int s = 0; s < S; ++s) {
-      const int n_neg = sm.sprog[1 + 3 * s], n = n_neg + sm.sprog[2 + 3 * s];
+      const int n = sm.sprog[1 + 3 * s] + sm.sprog[2 + 3 * s];
       for (int k = 0; k < n; ++k)
-        if (tq[k] <= nmax) ne = s + 1;
+        if (tq[k] <= kCols - T::kR) ne = s + 1;
+      tq += n;
+    }
+    sm.s_near_end[0] = ne;
+  }
+  __syncthreads();
+  const int near_end = sm.s_near_end[0];
+  if (tid < T::kG) {  // per thread group: the segment table
+    const int g = tid, nmax = T::near_max(g);
+    int4* st = sm.segtab + g * (sm.opstride / 2);
+    const int* tq = taps;
+    for (int s = 0; s < S; ++s) {
+      const int n_neg = sm.sprog[1 + 3 * s], n = n_neg + sm.sprog[2 + 3 * s];
       int a = 0, b = 0;  // leading tensor-memory taps of the two lists
-      while (a < n_neg && tq[a] <= nmax) ++a;
-      while (n_neg + b < n && tq[n_neg + b] <= nmax) ++b;
+      if (s < near_end) {
+        while (a < n_neg && tq[a] <= nmax) ++a;
+        while (n_neg + b < n && tq[n_neg + b] <= nmax) ++b;
+      }
       st[s] = make_int4(n_neg, n - n_neg, a | (b << 16), p.apply_gain ? sm.sprog[3 + 3 * s] : __float_as_int(1.0f));
       tq += n;
     }
-    sm.s_near_end[g] = ne;
   }
   // decode the taps for the thread groups (group g owns outputs RG g .. RG g + RG - 1 of a row)
+  int near_taps = 0;  // taps of the segments before near_end
+  for (int s = 0; s < near_end; ++s) near_taps += sm.sprog[1 + 3 * s] + sm.sprog[2 + 3 * s];
   for (int t = tid; t < T::kG * (ntaps + 2); t += T::kNT) {
     const int g = t / (ntaps + 2), k = t - g * (ntaps + 2);
     int op = 0;  // two slack words behind each list
     if (k < ntaps) {
       const int i = taps[k];
-      if (i <= T::near_max(g)) {
+      if (k < near_taps && i <= T::near_max(g)) {
         op = i;
       } else {
         const int o = i + T::kRG * g, A = o & 3, oal = o - A;
@@ -696,7 +718,7 @@ __device__ __noinline__ void compute_main(const TmParams& P, uint32_t tbase, int
     if (!begin_run<T>(P, sm, run, tid, r)) continue;
     stagger(q, stagger_ns);
     const int S = sm.sprog[0];
-    const int near_end = sm.s_near_end[g];
+    const int near_end = sm.s_near_end[0];
     for (int ti = 0; ti < r.n_tiles; ++ti) {
       const uint32_t row = smem_u32(sm.in_all + b * sm.bufw + m * T::kPitch);
       float yv[RG];
@@ -781,7 +803,7 @@ static const int g_stagger_ns = [] {
   const char* e = getenv("VND_TM_STAGGER_NS");
   return e ? atoi(e) : 2000;
 }();
-// VND_TM_SHAPE picks the kernel shape (see TmShape): 0 = 3 x 32, 1 = 2 x 48, 2 = 2 x 64, 3 = 2 x 32.
+// VND_TM_SHAPE picks the kernel shape (see TmShape and fir_tmem_launch): 0 = 3 x 32 (default), 1 = 2 x 48, 2 = 2 x 64, 3 = 2 x 32, 4 = 3 pipelined.
 static const int g_tm_shape = [] {
   const char* e = getenv("VND_TM_SHAPE");
   return e ? atoi(e) : VND_TM_DEFAULT_SHAPE;
@@ -811,6 +833,28 @@ static bool encode_rows(CUtensorMap* tm, const void* base, long long frames, lon
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Split every channel into equal runs so that the persistent CTAs finish together: pick the number of runs per
+// channel that minimises (waves of runs) x (tiles per run + two tiles of prologue).
+static void plan_runs(long long tiles, int channels, int sm_count, int* tiles_per_run, int* runs_per_channel) {
+  long long best_cost = -1;
+  int best_rpc = 1;
+  const long long rpc_lo = ceil_div<long long>(tiles, VND_TM_RUN_MAX);
+  long long rpc_hi = tiles / VND_TM_RUN_MIN;
+  if (rpc_hi < rpc_lo) rpc_hi = rpc_lo;
+  for (long long rpc = rpc_lo; rpc <= rpc_hi; ++rpc) {
+    const long long tpr = ceil_div<long long>(tiles, rpc);
+    const long long real_rpc = ceil_div<long long>(tiles, tpr);
+    const long long waves = ceil_div<long long>(real_rpc * channels, sm_count);
+    const long long cost = waves * (tpr + 2);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best_rpc = (int)real_rpc;
+    }
+  }
+  *tiles_per_run = (int)ceil_div<long long>(tiles, best_rpc);
+  *runs_per_channel = (int)ceil_div<long long>(tiles, *tiles_per_run);
 }
 
 // Runs the interior tiles of every channel and reports the frames covered per channel in
@@ -846,26 +890,7 @@ static int fir_tmem_launch_t(const FirParams& f, int max_prog_words, cudaStream_
   const long long tiles = (f.frames - span) / kTile + 1;
   if (tiles > 0x3fffffffLL / (f.channels > 0 ? f.channels : 1)) return VND_EUNSUPPORTED;
   P.tiles_per_channel = (int)tiles;
-  {  // split every channel into equal runs so that the persistent CTAs finish together: pick the number of
-     // runs per channel that minimises (waves of runs) x (tiles per run + two tiles of prologue)
-    long long best_cost = -1;
-    int best_rpc = 1;
-    const long long rpc_lo = ceil_div<long long>(tiles, VND_TM_RUN_MAX);
-    long long rpc_hi = tiles / VND_TM_RUN_MIN;
-    if (rpc_hi < rpc_lo) rpc_hi = rpc_lo;
-    for (long long rpc = rpc_lo; rpc <= rpc_hi; ++rpc) {
-      const long long tpr = ceil_div<long long>(tiles, rpc);
-      const long long real_rpc = ceil_div<long long>(tiles, tpr);
-      const long long waves = ceil_div<long long>(real_rpc * f.channels, di.sm_count);
-      const long long cost = waves * (tpr + 2);
-      if (best_cost < 0 || cost < best_cost) {
-        best_cost = cost;
-        best_rpc = (int)real_rpc;
-      }
-    }
-    P.tiles_per_run = (int)ceil_div<long long>(tiles, best_rpc);
-    P.runs_per_channel = (int)ceil_div<long long>(tiles, P.tiles_per_run);
-  }
+  plan_runs(tiles, f.channels, di.sm_count, &P.tiles_per_run, &P.runs_per_channel);
   P.n_runs = P.runs_per_channel * f.channels;
   VND_CUDA_OK(cudaFuncSetAttribute(fir_tmem_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = di.sm_count;
@@ -877,15 +902,47 @@ static int fir_tmem_launch_t(const FirParams& f, int max_prog_words, cudaStream_
   return VND_OK;
 }
 
+// Shapes measured in round 2 (148 channels x 28.8 M frames, Gsamples/s, all bit-exact; profiles/r02_summary.md):
+//   0: 3 x 32 outputs, rows of 96 (default)                       357
+//   1: 2 x 48 outputs, rows of 96                                 325
+//   2: 2 x 64 outputs, rows of 128, two tile buffers              338
+//   3: 2 x 32 outputs, rows of 64 (TMEM refill 8 words/output)    298
+//   4: shape 3 with software-pipelined tensor-memory taps         272 (235 before the loop exits kept ptxas from
+//      interleaving the adds of the landed and of the in-flight buffer)
+// Two compute warps per scheduler do not make the tensor-memory path faster in the kernel (they do in
+// tools/microbench/tmem_lat.cu), and a second tcgen05.ld in flight per warp slows the taps down even with the
+// intended instruction order, so the round-1 shape stays.
 int fir_tmem_launch(const FirParams& f, int max_prog_words, cudaStream_t st, long long* frames_done) {
   switch (g_tm_shape) {
     case 1: return fir_tmem_launch_t<TmShape<2, 48, 3, 200, 104>>(f, max_prog_words, st, frames_done);
     case 2: return fir_tmem_launch_t<TmShape<2, 64, 2, 216, 72>>(f, max_prog_words, st, frames_done);
     case 3: return fir_tmem_launch_t<TmShape<2, 32, 3, 200, 104>>(f, max_prog_words, st, frames_done);
-    case 4: return fir_tmem_launch_t<TmShape<2, 48, 3, 224, 56, true>>(f, max_prog_words, st, frames_done);
-    case 5: return fir_tmem_launch_t<TmShape<2, 32, 3, 200, 104, true>>(f, max_prog_words, st, frames_done);
+    case 4: return fir_tmem_launch_t<TmShape<2, 32, 3, 200, 104, true>>(f, max_prog_words, st, frames_done);
     default: return fir_tmem_launch_t<TmShape<3, 32, 3, 144, 80>>(f, max_prog_words, st, frames_done);
   }
+}
+
+// Debug / test aid (not part of the ABI in include/vnd_b200.h): the run plan of the default shape for a slab -
+// out[0] = tiles per run, out[1] = runs per channel, out[2] = frames per tile; bench.py uses it to place a parity
+// window across a run boundary.  Returns VND_EUNSUPPORTED when the slab would not take the tensor-memory kernel.
+extern "C" int vnd_debug_fir_plan(long long frames, int channels, int halo, int* out) {
+  using T = TmShape<3, 32, 3, 144, 80>;
+  if (!out || g_tm_shape != 0) return VND_EUNSUPPORTED;
+  halo = (halo + 3) & ~3;
+  int nblk = kRows + (halo + 4 + T::kR - 1) / T::kR;
+  const int fill_blocks = kRows + (kCols + T::kR - 1) / T::kR;
+  if (nblk < fill_blocks) nblk = fill_blocks;
+  const long long span = (long long)nblk * T::kR;
+  if (nblk > 256 || frames < span + 3LL * T::kTile) return VND_EUNSUPPORTED;
+  DeviceInfo di;
+  if (device_info(&di)) return VND_ECUDA;
+  const long long tiles = (frames - span) / T::kTile + 1;
+  int tpr = 0, rpc = 0;
+  plan_runs(tiles, channels, di.sm_count, &tpr, &rpc);
+  out[0] = tpr;
+  out[1] = rpc;
+  out[2] = T::kTile;
+  return VND_OK;
 }
 
 }  // namespace vnd

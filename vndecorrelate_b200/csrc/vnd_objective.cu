@@ -13,8 +13,9 @@
 //     amplitude-weighted sums, whose weights make an absolute error of 1e-7 rad irrelevant;
 //   * max|theta| IS ulp-sensitive (the penalty term multiplies it by ~1.6e3), but rounding is
 //     monotone, so max|theta| is attained at the frame with the largest |d|/|s| among frames with
-//     s >= 0 and among frames with s < 0.  The kernel tracks those two frames exactly and the host
-//     evaluates a correctly rounded float32 arctan2 for just those.
+//     s >= 0 and among frames with s < 0.  The kernel tracks those two frames exactly (track_ratio: the cross
+//     products are compared in float64, where they are exact) and the host evaluates a correctly rounded float32
+//     arctan2 for just those.
 //
 // Decomposition: CTA = (chunk of tiles, clip, candidate group).  A tile of both channels (+ the
 // filter halo for channel 0) is staged in shared memory once and reused by every candidate of the
@@ -89,6 +90,20 @@ __device__ __forceinline__ void obj_fma2(float& a0, float& a1, float b0, float b
   asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(ra));
 }
 
+// Ratio tracker: record (ad, as) when ad / as > bd / bs, i.e. when ad * bs > bd * as, decided EXACTLY: the product of
+// two float32 values is exact in float64 and cannot underflow there.  The float32 pre-test only filters frames that
+// are certainly below the record: rounding is monotone, so exact(ad * bs) > exact(bd * as) implies
+// fl(ad * bs) >= fl(bd * as) >= fl(fl(bd * as) * 0.99999f), and underflowed (zero) products pass the test too.
+// Records are rare (a logarithmic number per lane), so the float64 compare is almost never executed.
+__device__ __forceinline__ void track_ratio(float ad, float as, float& bd, float& bs) {
+  if (ad * bs >= (bd * as) * 0.99999f) {
+    if ((double)ad * (double)bs > (double)bd * (double)as) {  // ties keep the earlier frame
+      bd = ad;
+      bs = as;
+    }
+  }
+}
+
 struct LaneAcc {
   float sr, srt, srt2, srt3, slr, sll;
   float d_pos, s_pos, d_neg, s_neg;  // |d|, |s| of the frame with the largest |d|/|s| per sign of s
@@ -110,12 +125,8 @@ __device__ __forceinline__ void lane_acc_frame(LaneAcc& a, float l, float r_) {
   a.srt3 = fmaf(rt * th, th, a.srt3);
   a.slr = fmaf(l, r_, a.slr);
   a.sll = fmaf(l, l, a.sll);
-  // exact-enough ordering of the ratios by cross multiplication (ties keep the earlier frame)
-  if (s >= 0.0f) {
-    if (ad * a.s_pos > a.d_pos * as) { a.d_pos = ad; a.s_pos = as; }
-  } else {
-    if (ad * a.s_neg > a.d_neg * as) { a.d_neg = ad; a.s_neg = as; }
-  }
+  if (s >= 0.0f) track_ratio(ad, as, a.d_pos, a.s_pos);
+  else track_ratio(ad, as, a.d_neg, a.s_neg);
 }
 
 // Two frames at once with packed arithmetic.  The amplitude-weighted sums run in two interleaved
@@ -177,17 +188,10 @@ __device__ __forceinline__ void lane_acc_pair(LaneAcc2& a, float l0, float l1, f
   obj_fma2(v0, v1, l0, l1, a.sll[0], a.sll[1]);
   a.sll[0] = v0;
   a.sll[1] = v1;
-  // exact-enough ordering of the ratios by cross multiplication (ties keep the earlier frame)
-  if (s0 >= 0.0f) {
-    if (ad0 * a.s_pos > a.d_pos * as0) { a.d_pos = ad0; a.s_pos = as0; }
-  } else {
-    if (ad0 * a.s_neg > a.d_neg * as0) { a.d_neg = ad0; a.s_neg = as0; }
-  }
-  if (s1 >= 0.0f) {
-    if (ad1 * a.s_pos > a.d_pos * as1) { a.d_pos = ad1; a.s_pos = as1; }
-  } else {
-    if (ad1 * a.s_neg > a.d_neg * as1) { a.d_neg = ad1; a.s_neg = as1; }
-  }
+  if (s0 >= 0.0f) track_ratio(ad0, as0, a.d_pos, a.s_pos);
+  else track_ratio(ad0, as0, a.d_neg, a.s_neg);
+  if (s1 >= 0.0f) track_ratio(ad1, as1, a.d_pos, a.s_pos);
+  else track_ratio(ad1, as1, a.d_neg, a.s_neg);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -505,6 +509,13 @@ struct ObjPlan {
   size_t smem;
 };
 
+// Most chunks a clip's tiles are split into: enough for 16 waves of CTAs over all clips, never more than the tiles.
+static long long max_chunks(long long tiles, int n_clips, int sm_count) {
+  long long c = ceil_div<long long>((long long)sm_count * 16, n_clips > 0 ? n_clips : 1);
+  if (c > tiles) c = tiles;
+  return c < 1 ? 1 : c;
+}
+
 static int plan_objective(long long frames, int n_clips, int n_cand, int halo, int max_prog_words, ObjPlan* pl) {
   DeviceInfo di;
   int rc = device_info(&di);
@@ -520,14 +531,27 @@ static int plan_objective(long long frames, int n_clips, int n_cand, int halo, i
   if (cpg > n_cand) cpg = n_cand;
   if (cpg > 1024) cpg = 1024;
   const long long tiles = ceil_div<long long>(frames, OBJ_TILE);
-  // enough CTAs for ~4 waves of one CTA per SM: first split tiles into chunks, then candidates
+  // One CTA per SM at a time: the launch takes ceil(CTAs / SMs) waves of (tiles per chunk) tile passes over the
+  // candidates of a group.  First make the groups small enough for ~4 waves, then pick the split of the tiles into
+  // chunks that minimises waves x tiles per chunk, i.e. that leaves the smallest idle tail in the last wave (64 clips
+  // x 10 chunks = 640 CTAs on 148 SMs ran 5 waves for 4.3 waves of work; 37 chunks of 10 tiles run 16 full waves).
   const long long want = (long long)di.sm_count * 4;
-  long long n_chunks = ceil_div<long long>(want, (long long)n_clips * ceil_div(n_cand, cpg));
-  if (n_chunks > tiles) n_chunks = tiles;
-  if (n_chunks < 1) n_chunks = 1;
+  while ((long long)n_clips * tiles * ceil_div(n_cand, cpg) < want && cpg > 16) cpg = (cpg + 1) / 2;
+  const long long groups = ceil_div(n_cand, cpg);
+  long long n_chunks = 1, best = -1;
+  const long long cap = max_chunks(tiles, n_clips, di.sm_count);  // what objective_workspace_bytes sizes the partial blocks for
+  for (long long c = 1; c <= cap; ++c) {
+    const long long tpc_c = ceil_div<long long>(tiles, c);
+    const long long real_c = ceil_div<long long>(tiles, tpc_c);
+    const long long waves = ceil_div<long long>((long long)n_clips * real_c * groups, di.sm_count);
+    const long long cost = waves * tpc_c * 4096 + real_c;  // ties: fewer chunks (fewer partial blocks to combine)
+    if (best < 0 || cost < best) {
+      best = cost;
+      n_chunks = real_c;
+    }
+  }
   int tpc = (int)ceil_div<long long>(tiles, n_chunks);
   n_chunks = ceil_div<long long>(tiles, tpc);
-  while ((long long)n_clips * n_chunks * ceil_div(n_cand, cpg) < want && cpg > 16) cpg = (cpg + 1) / 2;
   pl->cand_per_group = cpg;
   pl->n_groups = ceil_div(n_cand, cpg);
   pl->tiles_per_chunk = tpc;
@@ -543,9 +567,7 @@ int objective_workspace_bytes(long long frames, int n_clips, int n_cand, size_t*
   int rc = device_info(&di);
   if (rc) return rc;
   const long long tiles = ceil_div<long long>(frames, OBJ_TILE);
-  long long chunks = (long long)di.sm_count * 4;
-  if (chunks > tiles) chunks = tiles;
-  if (chunks < 1) chunks = 1;
+  const long long chunks = max_chunks(tiles, n_clips, di.sm_count);
   *bytes = (size_t)n_clips * chunks * n_cand * OBJ_SLOTS * 8 + 256;
   return VND_OK;
 }
@@ -553,6 +575,8 @@ int objective_workspace_bytes(long long frames, int n_clips, int n_cand, size_t*
 int vn_objective_launch(const float* clips, long long frames, int n_clips, long long clip_stride, long long chan_stride,
                         const vnd_tap_program* cand, double* partials, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   if (n_clips == 0 || cand->channels == 0) return VND_OK;
+  // the reference takes max(|theta|) of the frames: an empty signal is a ValueError there (optimization.py:41-43)
+  VND_REQUIRE(frames > 0, VND_EINVAL, "objective of an empty signal (zero-size array to reduction operation maximum which has no identity)");
   int halo = cand->halo > 0 ? cand->halo : 0;
   if (halo > frames) halo = (int)frames;
   halo = (halo + 3) & ~3;

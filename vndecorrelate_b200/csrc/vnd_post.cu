@@ -637,19 +637,19 @@ __global__ void __launch_bounds__(256) scale_kernel(float* y, long long y_st, lo
 // the loads and the stores are coalesced.  Used to turn wide frame-interleaved slabs into planar
 // ones (and back) around the planar FIR kernel.
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, long long rows,
-                                                        long long cols) {
+                                                        long long cols, long long ld_src, long long ld_dst) {
   __shared__ float tile[32][33];
   const long long tiles_c = ceil_div<long long>(cols, 32);
   const long long tr = blockIdx.x / tiles_c, tc = blockIdx.x % tiles_c;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int j = ty; j < 32; j += 8) {
     const long long r = tr * 32 + j, c = tc * 32 + tx;
-    if (r < rows && c < cols) tile[j][tx] = src[r * cols + c];
+    if (r < rows && c < cols) tile[j][tx] = src[r * ld_src + c];
   }
   __syncthreads();
   for (int j = ty; j < 32; j += 8) {
     const long long c = tc * 32 + j, r = tr * 32 + tx;
-    if (r < rows && c < cols) dst[c * rows + r] = tile[tx][j];
+    if (r < rows && c < cols) dst[c * ld_dst + r] = tile[tx][j];
   }
 }
 
@@ -760,12 +760,17 @@ int haas_launch(const vnd_signal* x, const vnd_signal* out, int delay, int delay
   return after_launch("haas_kernel");
 }
 
-int transpose_launch(const float* src, float* dst, long long rows, long long cols, cudaStream_t st) {
+// src is (rows, cols) with row pitch ld_src, dst becomes (cols, rows) with row pitch ld_dst (elements)
+int transpose_launch_ld(const float* src, float* dst, long long rows, long long cols, long long ld_src, long long ld_dst, cudaStream_t st) {
   if (rows * cols == 0) return VND_OK;
   const long long blocks = ceil_div<long long>(rows, 32) * ceil_div<long long>(cols, 32);
   VND_REQUIRE(blocks < 0x7fffffffLL, VND_EUNSUPPORTED, "transpose grid too large");
-  transpose_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, rows, cols);
+  transpose_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, rows, cols, ld_src, ld_dst);
   return after_launch("transpose_kernel");
+}
+
+int transpose_launch(const float* src, float* dst, long long rows, long long cols, cudaStream_t st) {
+  return transpose_launch_ld(src, dst, rows, cols, cols, rows, st);
 }
 
 int stereo_op_launch(const vnd_signal* a, const vnd_signal* dry, int op, double width, const void* gains, cudaStream_t st) {

@@ -633,18 +633,19 @@ class _ClipBank:
         return out
 
 
-def optimize_velvet_noise_batch(*, input_signals, sample_rate_hz: int, duration_seconds: float, num_impulses: int, seed: int = 1,
+def optimize_velvet_noise_batch(*, input_signals=None, sample_rate_hz: int, duration_seconds: float, num_impulses: int, seed: int = 1,
                                 grid_size: int = 400, angle_limit: float = np.pi / 4, lambda_mean: float = 5.0, lambda_skew: float = 2.0,
                                 lambda_correlation: float = 15.0, lambda_penalty: float = 1e3, group=None, details: bool = False,
-                                _bank_factory=None):
+                                local_signals=None, total_clips: int | None = None, _bank_factory=None):
     """``optimize_velvet_noise`` (optimization.py:230-310) for MANY clips of equal length: returns the float64 array of
     optimised ``log_distribution_strength`` values, element ``i`` equal to what ``optimize_velvet_noise(input_signal=
     input_signals[i], ...)`` returns.
 
     ``input_signals``: a sequence of ``(frames, 2)`` arrays, a planar ``(n_clips, 2, frames)`` float32 array, or a CUDA
     tensor of that shape.  With ``torch.distributed`` initialised (one process per GPU) the clips are partitioned in
-    contiguous blocks over the ranks of ``group``; every rank must pass the SAME ``input_signals`` (only its block is
-    uploaded).  Data path per rank: grid scores of its clips (one launch over clips x grid) -> ONE all-gather of the
+    contiguous blocks over the ranks of ``group`` (``sharding.block_range``); every rank passes the SAME
+    ``input_signals`` (only its block is read and uploaded) - or, when the clips already live on the ranks, its own
+    block as ``local_signals`` (e.g. a resident CUDA tensor) together with ``total_clips``.  Data path per rank: grid scores of its clips (one launch over clips x grid) -> ONE all-gather of the
     float32 score matrix so that every rank holds all rows (``get_local_minima`` needs both neighbours of every grid
     point, optimization.py:120-128) -> lock-step Brent refinement of the local minima of its own clips -> one
     all-gather of the refined strengths.  ``details=True`` also returns the score matrix, the local-minima sets and
@@ -653,11 +654,23 @@ def optimize_velvet_noise_batch(*, input_signals, sample_rate_hz: int, duration_
 
     kw = dict(angle_limit=angle_limit, lambda_mean=lambda_mean, lambda_skew=lambda_skew, lambda_correlation=lambda_correlation,
               lambda_penalty=lambda_penalty)
-    n_clips = input_signals.shape[0] if (R.is_torch_tensor(input_signals) or (isinstance(input_signals, np.ndarray) and input_signals.ndim == 3)) \
-        else len(input_signals)
     rank, world = S._world(group)
-    lo, hi = S.block_range(n_clips, rank, world)
-    local = input_signals[lo:hi]
+    if local_signals is not None:
+        if total_clips is None:
+            raise ValueError("local_signals needs total_clips (the number of clips over all ranks)")
+        n_clips = int(total_clips)
+        lo, hi = S.block_range(n_clips, rank, world)
+        local = local_signals
+        n_local = local.shape[0] if (R.is_torch_tensor(local) or (isinstance(local, np.ndarray) and local.ndim == 3)) else len(local)
+        if n_local != hi - lo:
+            raise ValueError(f"rank {rank} of {world} owns clips [{lo}, {hi}) but local_signals holds {n_local}")
+    else:
+        if input_signals is None:
+            raise ValueError("pass input_signals (all clips) or local_signals (this rank's block)")
+        n_clips = input_signals.shape[0] if (R.is_torch_tensor(input_signals) or (isinstance(input_signals, np.ndarray) and input_signals.ndim == 3)) \
+            else len(input_signals)
+        lo, hi = S.block_range(n_clips, rank, world)
+        local = input_signals[lo:hi]
 
     def candidate(kappa):
         return VelvetNoise(sample_rate_hz=sample_rate_hz, duration_seconds=duration_seconds, num_impulses=num_impulses,

@@ -133,20 +133,48 @@ def device_program(prog, device):
 class _PinnedBlock:
     """One page-locked block of the output pool; goes back to the pool when the last array on it dies."""
 
-    __slots__ = ("ptr", "nbytes", "__weakref__")
+    __slots__ = ("ptr", "nbytes", "pid", "__weakref__")
 
     def __init__(self, ptr: int, nbytes: int):
-        self.ptr, self.nbytes = ptr, nbytes
+        self.ptr, self.nbytes, self.pid = ptr, nbytes, os.getpid()
 
     def __del__(self):
-        _pinned_pool_release(self.ptr, self.nbytes)
+        if self.pid == os.getpid():  # a forked child must not recycle pointers registered in its parent's CUDA context
+            _pinned_pool_release(self.ptr, self.nbytes)
 
 
 _POOL_LOCK = threading.RLock()  # re-entrant: a garbage collection inside the locked region may release another block
 _POOL_FREE: dict[int, list[int]] = {}   # block size -> free pointers
-_POOL_BYTES = [0]                       # page-locked bytes this pool has allocated
-_POOL_CAP = int(os.environ.get("VND_PINNED_POOL_MB", "512")) << 20
-_POOL_MAX_BLOCK = 32 << 20           # larger results take ordinary memory: pinning them costs more than it saves on a first call
+_POOL_BYTES = [0]                       # page-locked bytes this pool has allocated (free and in use)
+_POOL_CAP = [int(os.environ.get("VND_PINNED_POOL_MB", "512")) << 20]
+_POOL_WARNED = [False]
+
+
+def set_pinned_pool_cap(nbytes: int) -> None:
+    """Upper bound of the page-locked memory the result pool may hold (default 512 MB, ``VND_PINNED_POOL_MB``).
+    Results that do not fit come back on ordinary memory and are downloaded through the context's staging ring;
+    callers that stream GB-sized slabs raise the cap so that results are written by DMA at link speed."""
+    with _POOL_LOCK:
+        _POOL_CAP[0] = int(nbytes)
+    trim_pinned_pool(int(nbytes))
+
+
+def trim_pinned_pool(keep_bytes: int = 0) -> int:
+    """Give free blocks back to the OS (``cudaFreeHost``) until the pool holds at most ``keep_bytes``; returns the
+    bytes released.  Called automatically when a request does not fit under the cap."""
+    released = 0
+    with _POOL_LOCK:
+        for size in sorted(_POOL_FREE, reverse=True):
+            free = _POOL_FREE[size]
+            while free and _POOL_BYTES[0] > keep_bytes:
+                ptr = free.pop()
+                try:
+                    N.lib().vnd_host_free(C.c_void_p(ptr))
+                except Exception:  # interpreter shutdown
+                    pass
+                _POOL_BYTES[0] -= size
+                released += size
+    return released
 
 
 def _pinned_pool_release(ptr: int, nbytes: int) -> None:
@@ -157,30 +185,56 @@ def _pinned_pool_release(ptr: int, nbytes: int) -> None:
         pass
 
 
+def _pinned_pool_after_fork() -> None:
+    # the parent's blocks belong to the parent's CUDA context: forget them (nothing is freed in the child)
+    _POOL_FREE.clear()
+    _POOL_BYTES[0] = 0
+
+
+if hasattr(os, "register_at_fork"):
+    os.register_at_fork(after_in_child=_pinned_pool_after_fork)
+
+
 def pinned_empty(shape, dtype) -> np.ndarray:
     """``np.empty(shape, dtype)`` on page-locked memory from a recycling pool, so that the device-to-host copy of
     a result is one DMA at link speed instead of a staged copy into freshly mapped pages (which costs more
     than the kernels for the stereo files of BASELINE configs 1 and 2).  The array owns its block: it returns
-    to the pool when the array and its views are gone.  Falls back to ``np.empty`` for very large results or
-    when the pool is at its cap (``VND_PINNED_POOL_MB``, default 512)."""
+    to the pool when the array and its views are gone.  Blocks are power-of-two sized; when a request does not
+    fit under the cap (``set_pinned_pool_cap``), idle blocks of other sizes are released first, and if it still
+    does not fit the result is ordinary ``np.empty`` memory (a ``ResourceWarning`` says so once): correct, but
+    downloaded through the staging ring."""
     dt = np.dtype(dtype)
     count = int(np.prod(shape))
     nbytes = count * dt.itemsize
-    if nbytes == 0 or nbytes > _POOL_MAX_BLOCK:
+    if nbytes == 0:
         return np.empty(shape, dtype=dt)
     size = 1 << max(16, (nbytes - 1).bit_length())  # power-of-two blocks of at least 64 KB
+    if size > 1 << 30:  # above 1 GB round to 256 MB instead of doubling
+        size = -(-nbytes // (256 << 20)) * (256 << 20)
     ptr = None
     with _POOL_LOCK:
         free = _POOL_FREE.get(size)
         if free:
             ptr = free.pop()
-        elif _POOL_BYTES[0] + size <= _POOL_CAP:
-            _POOL_BYTES[0] += size
         else:
-            return np.empty(shape, dtype=dt)
+            if _POOL_BYTES[0] + size > _POOL_CAP[0]:
+                trim_pinned_pool(max(0, _POOL_CAP[0] - size))
+            if _POOL_BYTES[0] + size <= _POOL_CAP[0]:
+                _POOL_BYTES[0] += size
+            else:
+                if not _POOL_WARNED[0]:
+                    _POOL_WARNED[0] = True
+                    import warnings
+
+                    warnings.warn(f"vndecorrelate_b200: the page-locked result pool is at its cap ({_POOL_CAP[0] >> 20} MB); a {nbytes >> 20} MB "
+                                  "result uses pageable memory (slower download). Raise it with runtime.set_pinned_pool_cap().", ResourceWarning)
+                return np.empty(shape, dtype=dt)
     if ptr is None:
         p = C.c_void_p()
-        rc = N.lib().vnd_host_alloc(size, C.byref(p))
+        try:
+            rc = N.lib().vnd_ctx_host_alloc(HostContext.get().handle, size, C.byref(p))  # on the context's device, never on GPU 0 by accident
+        except N.VndError:
+            rc = -1
         if rc != 0 or not p.value:
             with _POOL_LOCK:
                 _POOL_BYTES[0] -= size
@@ -198,7 +252,7 @@ class PinnedArray:
     def __init__(self, shape, dtype=np.float32):
         self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
         ptr = C.c_void_p()
-        N.check(N.lib().vnd_host_alloc(self.nbytes, C.byref(ptr)), "vnd_host_alloc")
+        N.check(N.lib().vnd_ctx_host_alloc(HostContext.get().handle, self.nbytes, C.byref(ptr)), "vnd_ctx_host_alloc")
         self._ptr = ptr
         buf = (C.c_char * max(self.nbytes, 1)).from_address(ptr.value)
         self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
