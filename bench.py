@@ -669,7 +669,10 @@ def run_cfg4(env: Env, args, lib, N, R, VelvetNoise, C):
             raise SystemExit("bench cfg4: GPU output differs from the oracle")
         parity = f"bit-exact vs oracle on channels 0 and {Cg - 1}: {n} frames at the start, the middle and the end"
     steps = max(3, min(args.steps, 5))
+    sampler = ClockSampler(env.local_rank)
+    sampler.start()
     per_step, total_ms = env.timed_events(step, steps)
+    clocks = sampler.stop()
     value = env.world * Cg * L * steps / (total_ms * 1e-3) / 1e9
     kernel_ms = float(np.mean(per_step))
     peak, _ = measured_peak_gbs()
@@ -680,9 +683,10 @@ def run_cfg4(env: Env, args, lib, N, R, VelvetNoise, C):
     res = {
         "workload": f"BASELINE configs[3]: {CFG4_TOTAL_CHANNELS} ch x 10 min @ 96 kHz, 300 impulses over 0.3 s (halo 28 800 samples); "
                     f"{Cg} channels x {L} frames per GPU (channel-sharded, planar)",
-        "scaling": "weak", "value": value, "unit": UNIT, "ms": total_ms / steps, "steps": steps,
+        "scaling": "weak", "value": value, "unit": UNIT, "ms": total_ms / steps, "steps": steps, "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "kernel": "fir_tile_kernel<float, SEGMENTED, 1024 threads> (tile + 28 800-sample halo = 223 KB of shared memory per CTA)"},
+                     "kernel": "fir_tile_kernel<float, SEGMENTED, 1024 threads, 16 outputs per lane> (tile 16 384 + 28 800-sample halo = 177 KB "
+                               "of shared memory, one CTA per SM, packed FADD2)"},
         "lsu_pipe": {"achieved": lsu_bytes / (kernel_ms * 1e-3) / 1e9, "peak": lsu_peak, "unit": "GB/s", "frac": lsu_bytes / (kernel_ms * 1e-3) / 1e9 / lsu_peak,
                      "note": "the binding bound: 300 taps x 4 B per output through the 128 B/clk/SM shared-memory pipe = 31 Gsamples/s per GPU at 1965 MHz"},
         "parity": parity,
@@ -740,12 +744,15 @@ def run_cfg5(env: Env, args, lib, N, R, OPT):
     kappa, info = optimise(resident)  # warm-up (NCCL communicator, arenas)
     steps = max(1, min(args.steps, 2))
     launches0 = N.launch_count()
+    sampler = ClockSampler(env.local_rank)
     env.barrier()
+    sampler.start()
     t0 = time.perf_counter()
     for _ in range(steps):
         kappa, info = optimise(resident)
     torch.cuda.synchronize()
     dt = env.max_over_ranks(time.perf_counter() - t0) / steps
+    clocks = sampler.stop()
     launches = int(env.sum_over_ranks(N.launch_count() - launches0)) // steps
     evals = int(env.sum_over_ranks(info["evaluations_local"]))
     # end to end: host clips in (the rank uploads its block inside the call)
@@ -762,7 +769,10 @@ def run_cfg5(env: Env, args, lib, N, R, OPT):
     prog = kappa_family_program(np.linspace(0.0, 1.0, grid), sample_rate_hz=FS, duration_seconds=0.03, num_impulses=30,
                                 envelope=(0.85, 0.55, 0.35, 0.2), seed=1, frames=frames)
     OPT.vn_objective_partials(block, prog)
+    sampler = ClockSampler(env.local_rank)
+    sampler.start()
     per_step, _ = env.timed_events(lambda: OPT.vn_objective_partials(block, prog), 3)
+    k_clocks = sampler.stop()
     k_ms = float(np.mean(per_step))
     k_evals = (hi - lo) * grid
     frame_evals = k_evals * frames
@@ -792,12 +802,12 @@ def run_cfg5(env: Env, args, lib, N, R, OPT):
                     "grid scan + lock-step Brent refinement of every local minimum",
         "scaling": "strong (the clips are sharded over the ranks; one all-gather of the float32 score matrix, one of the refined strengths)",
         "value": evals / dt, "unit": "objective evaluations/s (clip x strength, grid + refinement)", "ms": dt * 1e3, "steps": steps,
-        "clips": n_clips, "clips_per_s": n_clips / dt, "evaluations": evals, "kernel_launches": launches,
+        "clips": n_clips, "clips_per_s": n_clips / dt, "evaluations": evals, "kernel_launches": launches, "clocks": clocks,
         "collective": f"NCCL all_gather_into_tensor, {env.world} ranks" if env.world > 1 else "none (one rank)",
         "scores_sha256": digest, "argmin_first8": info["argmin"][:8], "local_minima_first8": [len(m) for m in info["local_minima"][:8]],
         "kappa_first4": [float(k) for k in kappa[:4]],
         "grid_kernel": {"kernel": "vn_objective_kernel", "ms": k_ms, "evaluations_per_s_per_gpu": k_evals / (k_ms * 1e-3),
-                        "frame_evaluations_per_s_per_gpu": frame_evals / (k_ms * 1e-3)},
+                        "frame_evaluations_per_s_per_gpu": frame_evals / (k_ms * 1e-3), "clocks": k_clocks},
         "roofline": {"bound": "hbm", "achieved": hbm_bytes / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": hbm_bytes / (k_ms * 1e-3) / 1e9 / peak,
                      "traffic": None, "note": "not the binding bound: every clip is read once per tile and reused by all strengths from shared memory"},
         "lsu_pipe": {"achieved": lsu_bytes / (k_ms * 1e-3) / 1e9, "peak": lsu_peak, "unit": "GB/s", "frac": lsu_bytes / (k_ms * 1e-3) / 1e9 / lsu_peak,

@@ -148,6 +148,22 @@ int vnd_haas_dev(const vnd_signal* x, const vnd_signal* out, int32_t delay, int3
 int vnd_stereo_op_dev(const vnd_signal* a, const vnd_signal* dry, int32_t op, double width,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Normalisers and polar form beyond what VelvetNoise itself uses (utils/dsp.py:71-109, :374-422).  Signals are
+ * contiguous 1-D (ndim = 1) or C-order (frames, channels) arrays (ndim = 2), F32 or F64.
+ *   rms_normalize: STEREO mode and 1-D signals (both statistics with axis=None: numpy's pairwise summation order is
+ *       reproduced bit for bit); 2-D DUAL_MONO keeps using vnd_stereo_op op 4 (numpy's axis-0 order).
+ *   peak_normalize: every mode.
+ *   polar_coordinates: radii, folded (or full) angles and amplitude weights of a stereo pair; weights may be NULL.
+ *       Radii and weights are bit-exact, angles within 2 ulp of numpy's arctan2.
+ * Workspace: vnd_dsp_workspace(largest element count) bytes. */
+int vnd_dsp_workspace(int64_t elems, size_t* bytes);
+int vnd_rms_normalize_dev(const vnd_signal* x, int32_t x_ndim, const vnd_signal* y, int32_t y_ndim, int32_t stereo_mode, double epsilon,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int vnd_peak_normalize_dev(const vnd_signal* y, int32_t ndim, int32_t stereo_mode, double epsilon, void* workspace, size_t workspace_bytes,
+                           void* stream);
+int vnd_polar_dev(const void* left, const void* right, int64_t n, int32_t dtype, int32_t mode_ms, int32_t semicircular, int32_t normalize,
+                  void* radii, void* thetas, void* weights, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Batched stereo-image objective for velvet-noise candidates (optimization.py:46-105 evaluated as
  * optimization.py:108-117 does, for the candidates optimization.py:260-272 builds: channel 0
  * filtered, channel 1 passed through, LR, no normaliser).
@@ -199,6 +215,11 @@ int vnd_vn_decorrelate_host(vnd_ctx* ctx, const vnd_signal* x, const vnd_signal*
 int vnd_haas_host(vnd_ctx* ctx, const vnd_signal* x, const vnd_signal* out, int32_t delay,
                   int32_t delayed_channel, int32_t mode_ms, int32_t mono, int32_t use_width, double width);
 int vnd_stereo_op_host(vnd_ctx* ctx, const vnd_signal* a, const vnd_signal* dry, int32_t op, double width);
+int vnd_rms_normalize_host(vnd_ctx* ctx, const vnd_signal* x, int32_t x_ndim, const vnd_signal* y, int32_t y_ndim, int32_t stereo_mode,
+                           double epsilon);
+int vnd_peak_normalize_host(vnd_ctx* ctx, const vnd_signal* y, int32_t ndim, int32_t stereo_mode, double epsilon);
+int vnd_polar_host(vnd_ctx* ctx, const void* left, const void* right, int64_t n, int32_t dtype, int32_t mode_ms, int32_t semicircular,
+                   int32_t normalize, void* radii, void* thetas, void* weights);
 int vnd_vn_objective_batch_host(vnd_ctx* ctx, const float* clips, int64_t frames, int32_t n_clips,
                                 int64_t clip_stride, int64_t chan_stride, const vnd_tap_program* cand,
                                 double* partials);

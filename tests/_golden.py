@@ -64,3 +64,18 @@ def wav(name: str):
 def same_bits(a: np.ndarray, b: np.ndarray) -> bool:
     """Bit equality including dtype and shape (distinguishes -0.0 from +0.0)."""
     return a.dtype == b.dtype and a.shape == b.shape and np.ascontiguousarray(a).tobytes() == np.ascontiguousarray(b).tobytes()
+
+
+def dsp_inputs(kind: str, seed: int, n: int, dtype):
+    """The seeded inputs of one case of dsp_extra.json (same draws as tests/golden/make_golden_r02.py::dsp_inputs)."""
+    rng = np.random.default_rng(seed)
+    if kind == "polar_coordinates":
+        return (rng.standard_normal(n) * 0.3).astype(dtype), (rng.standard_normal(n) * 0.3).astype(dtype)
+    return (rng.standard_normal((n, 2)) * 0.3).astype(dtype), (rng.standard_normal((n, 2)) * 0.1).astype(dtype)
+
+
+@functools.lru_cache(maxsize=None)
+def dsp_extra():
+    man = json.load(open(os.path.join(GOLDEN, "dsp_extra.json")))
+    arr = np.load(os.path.join(GOLDEN, "dsp_extra.npz"))
+    return man, arr

@@ -576,3 +576,46 @@ def test_interval_grid_family_is_bitwise_the_single_strength_grid():
         for i in range(0, len(sub), 7):
             w1, s1 = T._interval_grid(float(sub[i]), n_imp, fir_len)
             assert np.array_equal(w1, w[i]) and np.array_equal(s1, s[i])
+
+
+def test_array_brent_equals_the_coroutine_abscissa_by_abscissa():
+    """optimization._BrentBatch (every minimiser of every clip advanced by array arithmetic) against the coroutine
+    restatement of scipy's bounded minimiser - which the tests above pin to scipy itself - on 2000 float32-valued,
+    piecewise-constant noisy objectives (the shape the rounded-tap objective has) and 300 float64 ones: same abscissae
+    in the same order, same x / fun / nfev, fun in the objective's dtype."""
+    from vndecorrelate_b200 import optimization as OPT
+
+    rng = np.random.default_rng(0)
+
+    def make(dtype):
+        c, s, step = rng.uniform(0, 1), rng.uniform(0.1, 50), rng.choice([0, 1e-3, 1e-2, 5e-2])
+        off, tab = rng.uniform(600, 620), rng.standard_normal(4096) * rng.uniform(0, 1e-3)
+
+        def f(x):
+            xx = np.floor(x / step) * step if step > 0 else x
+            return dtype(off + s * (xx - c) ** 2 + tab[int(abs(x) * 1e6) % 4096])
+
+        return f
+
+    for dtype, n in ((np.float32, 2000), (np.float64, 300)):
+        fs = [make(dtype) for _ in range(n)]
+        lo = rng.uniform(0, 0.9, n)
+        hi = lo + rng.uniform(1e-3, 0.2, n)
+        seq_a = [[] for _ in range(n)]
+        seq_b = [[] for _ in range(n)]
+
+        def batch_a(xs, ids):
+            for x, i in zip(xs, ids):
+                seq_a[i].append(x)
+            return [fs[i](x) for x, i in zip(xs, ids)]
+
+        def batch_b(xs, ids):
+            for x, i in zip(xs, ids):
+                seq_b[i].append(float(x))
+            return np.array([fs[i](float(x)) for x, i in zip(xs, ids)], dtype=dtype)
+
+        want = OPT.lockstep_minimize(list(zip(lo, hi)), batch_a, xatol=1e-4, with_ids=True)
+        x, fun, nfev = OPT.lockstep_minimize_arrays(lo, hi, batch_b, xatol=1e-4)
+        assert fun.dtype == dtype
+        for i in range(n):
+            assert seq_a[i] == seq_b[i] and want[i].x == x[i] and want[i].fun == fun[i] and want[i].nfev == nfev[i], i

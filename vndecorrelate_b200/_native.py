@@ -13,7 +13,7 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libvnd_b200.so")
+LIB_PATH = os.environ.get("VND_B200_LIB") or os.path.join(_HERE, "_lib", "libvnd_b200.so")  # the override is for A/B builds of the kernels
 BUILD_SCRIPT = os.path.join(_HERE, "csrc", "build.sh")
 
 VND_OK, VND_EINVAL, VND_ECUDA, VND_EUNSUPPORTED, VND_ENOMEM, VND_EPROGRAM = 0, -1, -2, -3, -4, -5
@@ -79,6 +79,15 @@ SIGNATURES = {
     "vnd_colsumsq_seq_f32_dev": (C.c_int, [_P(SignalStruct), C.c_void_p, C.c_void_p]),
     "vnd_haas_dev": (C.c_int, [_P(SignalStruct), _P(SignalStruct), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p]),
     "vnd_stereo_op_dev": (C.c_int, [_P(SignalStruct), _P(SignalStruct), C.c_int32, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "vnd_dsp_workspace": (C.c_int, [C.c_int64, _P(C.c_size_t)]),
+    "vnd_rms_normalize_dev": (C.c_int, [_P(SignalStruct), C.c_int32, _P(SignalStruct), C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "vnd_peak_normalize_dev": (C.c_int, [_P(SignalStruct), C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "vnd_polar_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_size_t, C.c_void_p]),
+    "vnd_rms_normalize_host": (C.c_int, [C.c_void_p, _P(SignalStruct), C.c_int32, _P(SignalStruct), C.c_int32, C.c_int32, C.c_double]),
+    "vnd_peak_normalize_host": (C.c_int, [C.c_void_p, _P(SignalStruct), C.c_int32, C.c_int32, C.c_double]),
+    "vnd_polar_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]),
     "vnd_objective_workspace": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _P(C.c_size_t)]),
     "vnd_vn_objective_batch_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int64, _P(TapProgramStruct), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "vnd_haas_objective_batch_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -35,6 +35,11 @@ int vn_objective_launch(const float* clips, long long frames, int n_clips, long 
                         const vnd_tap_program* cand, double* partials, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int haas_objective_launch(const void* clips, int clip_dtype, long long frames, int n_clips, long long clip_stride, long long chan_stride,
                           const int* delays, int n_cand, double* partials, cudaStream_t st);
+size_t dsp_workspace_bytes(long long elems);
+int rms_normalize_launch(const vnd_signal* x, const vnd_signal* y, int x_ndim, int y_ndim, int stereo_mode, double eps, void* ws, cudaStream_t st);
+int peak_normalize_launch(const vnd_signal* y, int ndim, int stereo_mode, double eps, void* ws, cudaStream_t st);
+int polar_launch(const void* l, const void* r, long long n, int dtype, int mode_ms, int semicircular, int normalize, void* radii, void* thetas,
+                 void* weights, void* ws, cudaStream_t st);
 
 // ---- error state ----------------------------------------------------------------------------
 static thread_local char t_error[512] = "";
@@ -266,6 +271,49 @@ extern "C" int vnd_haas_objective_batch_dev(const void* clips, int32_t clip_dtyp
   return haas_objective_launch(clips, clip_dtype, frames, n_clips, clip_stride, chan_stride, delays, n_cand, partials, (cudaStream_t)stream);
 }
 
+static int check_flat(const vnd_signal* s, int ndim, const char* name) {
+  int rc;
+  if ((rc = check_signal(s, name))) return rc;
+  VND_REQUIRE(ndim == 1 || ndim == 2, VND_EINVAL, "%s: ndim must be 1 or 2", name);
+  if (ndim == 1) VND_REQUIRE(s->stride_t == 1 || s->frames <= 1, VND_EUNSUPPORTED, "%s must be contiguous", name);
+  else VND_REQUIRE((s->stride_c == 1 || s->channels <= 1) && (s->stride_t == s->channels || s->frames <= 1), VND_EUNSUPPORTED,
+                   "%s must be a contiguous C-order (frames, channels) array", name);
+  return VND_OK;
+}
+
+extern "C" int vnd_dsp_workspace(int64_t elems, size_t* bytes) {
+  VND_REQUIRE(bytes != nullptr && elems >= 0, VND_EINVAL, "bad argument");
+  *bytes = dsp_workspace_bytes(elems);
+  return VND_OK;
+}
+
+extern "C" int vnd_rms_normalize_dev(const vnd_signal* x, int32_t x_ndim, const vnd_signal* y, int32_t y_ndim, int32_t stereo_mode, double epsilon,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = check_flat(x, x_ndim, "input_signal")) || (rc = check_flat(y, y_ndim, "output_signal"))) return rc;
+  VND_REQUIRE(x->dtype == y->dtype, VND_EINVAL, "input and output must have the same dtype");
+  const long long nx = x->frames * (long long)(x_ndim == 1 ? 1 : x->channels), ny = y->frames * (long long)(y_ndim == 1 ? 1 : y->channels);
+  VND_REQUIRE(workspace != nullptr && workspace_bytes >= dsp_workspace_bytes(nx > ny ? nx : ny), VND_ENOMEM, "dsp workspace too small");
+  return rms_normalize_launch(x, y, x_ndim, y_ndim, stereo_mode, epsilon, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int vnd_peak_normalize_dev(const vnd_signal* y, int32_t ndim, int32_t stereo_mode, double epsilon, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  int rc;
+  if ((rc = check_flat(y, ndim, "input_signal"))) return rc;
+  VND_REQUIRE(workspace != nullptr && workspace_bytes >= dsp_workspace_bytes(0), VND_ENOMEM, "dsp workspace too small");
+  return peak_normalize_launch(y, ndim, stereo_mode, epsilon, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int vnd_polar_dev(const void* left, const void* right, int64_t n, int32_t dtype, int32_t mode_ms, int32_t semicircular, int32_t normalize,
+                             void* radii, void* thetas, void* weights, void* workspace, size_t workspace_bytes, void* stream) {
+  VND_REQUIRE(n >= 0, VND_EINVAL, "negative length");
+  VND_REQUIRE(dtype == VND_F32 || dtype == VND_F64, VND_EINVAL, "unknown dtype %d", dtype);
+  VND_REQUIRE(n == 0 || (left && right && radii && thetas), VND_EINVAL, "null buffer");
+  VND_REQUIRE(workspace != nullptr && workspace_bytes >= dsp_workspace_bytes(n), VND_ENOMEM, "dsp workspace too small");
+  return polar_launch(left, right, n, dtype, mode_ms, semicircular, normalize, radii, thetas, weights, workspace, (cudaStream_t)stream);
+}
+
 // ================================================================================================
 // host entry points
 // ================================================================================================
@@ -440,6 +488,70 @@ extern "C" int vnd_ctx_host_alloc(vnd_ctx* ctx, size_t bytes, void** ptr) {
 
 extern "C" int vnd_host_free(void* ptr) {
   if (ptr) VND_CUDA_OK(cudaFreeHost(ptr));
+  return VND_OK;
+}
+
+extern "C" int vnd_rms_normalize_host(vnd_ctx* ctx, const vnd_signal* x, int32_t x_ndim, const vnd_signal* y, int32_t y_ndim, int32_t stereo_mode,
+                                      double epsilon) {
+  VND_ENTER(ctx);
+  int rc;
+  if ((rc = check_flat(x, x_ndim, "input_signal")) || (rc = check_flat(y, y_ndim, "output_signal"))) return rc;
+  const size_t es = esize(x->dtype);
+  const size_t nx = (size_t)x->frames * (x_ndim == 1 ? 1 : x->channels), ny = (size_t)y->frames * (y_ndim == 1 ? 1 : y->channels);
+  cudaStream_t st = ctx->streams[0];
+  void *dx = nullptr, *dy = nullptr, *work = nullptr;
+  const size_t wbytes = dsp_workspace_bytes((long long)(nx > ny ? nx : ny));
+  if ((rc = arena(ctx, S_IN, nx * es, &dx)) || (rc = arena(ctx, S_OUT, ny * es, &dy)) || (rc = arena(ctx, S_WORK, wbytes, &work))) return rc;
+  if (nx) VND_CUDA_OK(cudaMemcpyAsync(dx, x->data, nx * es, cudaMemcpyHostToDevice, st));
+  if (ny) VND_CUDA_OK(cudaMemcpyAsync(dy, y->data, ny * es, cudaMemcpyHostToDevice, st));
+  vnd_signal xd = *x, yd = *y;
+  xd.data = dx;
+  yd.data = dy;
+  if ((rc = vnd_rms_normalize_dev(&xd, x_ndim, &yd, y_ndim, stereo_mode, epsilon, work, wbytes, st))) return rc;
+  if (ny) VND_CUDA_OK(cudaMemcpyAsync(y->data, dy, ny * es, cudaMemcpyDeviceToHost, st));
+  VND_CUDA_OK(cudaStreamSynchronize(st));
+  return VND_OK;
+}
+
+extern "C" int vnd_peak_normalize_host(vnd_ctx* ctx, const vnd_signal* y, int32_t ndim, int32_t stereo_mode, double epsilon) {
+  VND_ENTER(ctx);
+  int rc;
+  if ((rc = check_flat(y, ndim, "input_signal"))) return rc;
+  const size_t es = esize(y->dtype), ny = (size_t)y->frames * (ndim == 1 ? 1 : y->channels);
+  cudaStream_t st = ctx->streams[0];
+  void *dy = nullptr, *work = nullptr;
+  const size_t wbytes = dsp_workspace_bytes(0);
+  if ((rc = arena(ctx, S_IN, ny * es, &dy)) || (rc = arena(ctx, S_WORK, wbytes, &work))) return rc;
+  if (ny) VND_CUDA_OK(cudaMemcpyAsync(dy, y->data, ny * es, cudaMemcpyHostToDevice, st));
+  vnd_signal yd = *y;
+  yd.data = dy;
+  if ((rc = vnd_peak_normalize_dev(&yd, ndim, stereo_mode, epsilon, work, wbytes, st))) return rc;
+  if (ny) VND_CUDA_OK(cudaMemcpyAsync(y->data, dy, ny * es, cudaMemcpyDeviceToHost, st));
+  VND_CUDA_OK(cudaStreamSynchronize(st));
+  return VND_OK;
+}
+
+extern "C" int vnd_polar_host(vnd_ctx* ctx, const void* left, const void* right, int64_t n, int32_t dtype, int32_t mode_ms, int32_t semicircular,
+                              int32_t normalize, void* radii, void* thetas, void* weights) {
+  VND_ENTER(ctx);
+  int rc;
+  VND_REQUIRE(n >= 0, VND_EINVAL, "negative length");
+  VND_REQUIRE(dtype == VND_F32 || dtype == VND_F64, VND_EINVAL, "unknown dtype %d", dtype);
+  if (n == 0) return VND_OK;
+  VND_REQUIRE(left && right && radii && thetas, VND_EINVAL, "null buffer");
+  const size_t bytes = (size_t)n * esize(dtype);
+  cudaStream_t st = ctx->streams[0];
+  void *din = nullptr, *dout = nullptr, *work = nullptr;
+  const size_t wbytes = dsp_workspace_bytes(n);
+  if ((rc = arena(ctx, S_IN, 2 * bytes, &din)) || (rc = arena(ctx, S_OUT, 3 * bytes, &dout)) || (rc = arena(ctx, S_WORK, wbytes, &work))) return rc;
+  char *dl = (char*)din, *dr = dl + bytes, *drad = (char*)dout, *dth = drad + bytes, *dw = dth + bytes;
+  VND_CUDA_OK(cudaMemcpyAsync(dl, left, bytes, cudaMemcpyHostToDevice, st));
+  VND_CUDA_OK(cudaMemcpyAsync(dr, right, bytes, cudaMemcpyHostToDevice, st));
+  if ((rc = vnd_polar_dev(dl, dr, n, dtype, mode_ms, semicircular, normalize, drad, dth, weights ? dw : nullptr, work, wbytes, st))) return rc;
+  VND_CUDA_OK(cudaMemcpyAsync(radii, drad, bytes, cudaMemcpyDeviceToHost, st));
+  VND_CUDA_OK(cudaMemcpyAsync(thetas, dth, bytes, cudaMemcpyDeviceToHost, st));
+  if (weights) VND_CUDA_OK(cudaMemcpyAsync(weights, dw, bytes, cudaMemcpyDeviceToHost, st));
+  VND_CUDA_OK(cudaStreamSynchronize(st));
   return VND_OK;
 }
 

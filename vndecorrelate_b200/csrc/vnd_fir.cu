@@ -39,6 +39,23 @@ __device__ __forceinline__ float step_add(float acc, TIn x) {
   else return fadd(acc, x);
 }
 
+// Packed float32 arithmetic (sm_100+: FADD2 / FMUL2, two IEEE round-to-nearest operations per instruction on an aligned
+// register pair): the same bits as two scalar operations in half the issue slots.  The tile kernel issues one LDS and
+// one add per (output, tap) pair; with packed adds the long-filter configuration (300 taps, shared-memory pipe bound)
+// spends 1.5 instead of 2 issue slots per pair.
+typedef unsigned long long fir_pair_t;
+#define VND_FIR_PACKED(name, op)                                                   \
+  __device__ __forceinline__ void name(float& a0, float& a1, float b0, float b1) { \
+    fir_pair_t ra, rb;                                                             \
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));                   \
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));                   \
+    asm(op ".rn.f32x2 %0, %0, %1;" : "+l"(ra) : "l"(rb));                         \
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(ra));                  \
+  }
+VND_FIR_PACKED(fir_add2, "add")
+VND_FIR_PACKED(fir_sub2, "sub")
+VND_FIR_PACKED(fir_mul2, "mul")
+
 // Runs one channel's tap program for R outputs per lane.  `px` points at the staged sample of
 // this lane's first output; consecutive outputs of the lane are `STRIDE` samples apart.
 template <typename TIn, int MODE, int R, int STRIDE>
@@ -57,24 +74,51 @@ __device__ __forceinline__ void run_program(const TIn* __restrict__ px, const in
       float acc[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) acc[r] = 0.0f;
-      for (int k = 0; k < n_neg; ++k) {
-        const TIn* q = px + tp[k];
+      if constexpr (!is_f64<TIn>::value && (R % 2 == 0)) {  // float32: packed adds, the loads of a tap issued together
+        for (int k = 0; k < n_neg; ++k) {
+          const TIn* q = px + tp[k];
+          float t[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = step_sub<TIn>(acc[r], q[r * STRIDE]);
+          for (int r = 0; r < R; ++r) t[r] = q[r * STRIDE];
+#pragma unroll
+          for (int r = 0; r < R; r += 2) fir_sub2(acc[r], acc[r + 1], t[r], t[r + 1]);
+        }
+        tp += n_neg;
+        for (int k = 0; k < n_pos; ++k) {
+          const TIn* q = px + tp[k];
+          float t[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) t[r] = q[r * STRIDE];
+#pragma unroll
+          for (int r = 0; r < R; r += 2) fir_add2(acc[r], acc[r + 1], t[r], t[r + 1]);
+        }
+        tp += n_pos;
+        if (apply_gain) {
+#pragma unroll
+          for (int r = 0; r < R; r += 2) fir_mul2(acc[r], acc[r + 1], gain, gain);
+        }
+#pragma unroll
+        for (int r = 0; r < R; r += 2) fir_add2(yv[r], yv[r + 1], acc[r], acc[r + 1]);
+      } else {
+        for (int k = 0; k < n_neg; ++k) {
+          const TIn* q = px + tp[k];
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r] = step_sub<TIn>(acc[r], q[r * STRIDE]);
+        }
+        tp += n_neg;
+        for (int k = 0; k < n_pos; ++k) {
+          const TIn* q = px + tp[k];
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r] = step_add<TIn>(acc[r], q[r * STRIDE]);
+        }
+        tp += n_pos;
+        if (apply_gain) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r] = fmul(acc[r], gain);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) yv[r] = fadd(yv[r], acc[r]);
       }
-      tp += n_neg;
-      for (int k = 0; k < n_pos; ++k) {
-        const TIn* q = px + tp[k];
-#pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = step_add<TIn>(acc[r], q[r * STRIDE]);
-      }
-      tp += n_pos;
-      if (apply_gain) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = fmul(acc[r], gain);
-      }
-#pragma unroll
-      for (int r = 0; r < R; ++r) yv[r] = fadd(yv[r], acc[r]);
     }
   } else {
     constexpr bool kF64 = is_f64<TIn>::value || MODE == MODE_ASC64;
@@ -361,6 +405,39 @@ static int launch_tile_nt(const FirParams& p, size_t smem, int nt, cudaStream_t 
   }
 }
 
+// Long filters (halo beyond 4096 samples, e.g. 300 impulses over 0.3 s @ 96 kHz: BASELINE config 4): tile + halo
+// fills the SM's shared memory, so ONE CTA of 32 warps runs per SM.  R outputs per lane and pass; the tile is a whole
+// number of passes for all 32 warps (round 1 ran 28 672 outputs = 3.5 passes of R = 8: half of the warps idled
+// through the fourth pass), and a larger R spreads the tap-index load and the loop overhead of a tap over more outputs.
+// Measured on 64 channels x 57.6 M frames (Gsamples/s, shared-memory pipe busy): round 1 (R = 8, 3.5 passes, scalar adds)
+// 25.1 / 81 %; R = 8 25.3 / 81 %; R = 12 26.0 / 84 %; R = 16 (one pass of 16 384 outputs) 27.5 / 89 %.
+// VND_LONG_R picks R in {8, 12, 16} (default 16).
+static int long_filter_r() {
+  static const int r = [] {
+    const char* e = getenv("VND_LONG_R");
+    const int v = e ? atoi(e) : 16;
+    return (v == 8 || v == 12 || v == 16) ? v : 16;
+  }();
+  return r;
+}
+static int plan_long_tile(int halo, int max_prog_words, int r, size_t* smem) {
+  const long long budget = (long long)kMaxDynSmem - 16 - 16 - (long long)max_prog_words * 4;
+  const long long per_pass = 32LL * 32 * r;
+  const long long tile = (budget / 4 - halo) / per_pass * per_pass;
+  if (tile <= 0) return 0;
+  *smem = 16 + (((size_t)(tile + halo) * 4 + 15) & ~(size_t)15) + (size_t)max_prog_words * 4;
+  return (int)tile;
+}
+template <int R>
+static int launch_long_tile(const FirParams& p, size_t smem, cudaStream_t st) {
+  auto k = fir_tile_kernel<float, MODE_SEG, 1024, R>;
+  VND_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long blocks = (long long)p.tiles_per_channel * p.channels;
+  VND_REQUIRE(blocks < 0x7fffffffLL, VND_EUNSUPPORTED, "grid too large (%lld CTAs)", blocks);
+  k<<<(unsigned)blocks, 1024, smem, st>>>(p);
+  return after_launch("fir_tile_kernel");
+}
+
 template <typename TIn, int MODE>
 static int launch_direct(const FirParams& p, cudaStream_t st) {
   DeviceInfo di;
@@ -438,6 +515,17 @@ int sparse_fir_launch(const vnd_signal* x, const vnd_signal* y, const vnd_tap_pr
   if (!f64 && mode == MODE_SEG && !g_disable_window) {  // planar float32 slabs too short for the above
     const int rc = fir_window_launch(p, max_prog_words, st);
     if (rc != VND_EUNSUPPORTED) return rc;
+  }
+  if (!f64 && mode == MODE_SEG && p.halo > 4096 && p.frames >= 4LL * p.halo) {  // long filters on long signals
+    const int r = long_filter_r();
+    const int tile = plan_long_tile(p.halo, max_prog_words, r, &smem);
+    if (tile > 0) {
+      p.tile = tile;
+      p.tiles_per_channel = (int)ceil_div<long long>(p.frames, p.tile);
+      if (r == 8) return launch_long_tile<8>(p, smem, st);
+      if (r == 12) return launch_long_tile<12>(p, smem, st);
+      return launch_long_tile<16>(p, smem, st);
+    }
   }
   p.tile = plan_tile(p.halo, elem, max_prog_words, p.frames, &nt, &smem);
   if (p.tile == 0) {

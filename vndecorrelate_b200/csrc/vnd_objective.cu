@@ -22,194 +22,15 @@
 // group; each WARP owns whole candidates (no block-level reduction, no __syncthreads in the
 // candidate loop), reduces with warp shuffles and accumulates float64 partials in shared memory.
 
-#include "vnd_common.cuh"
+#include <stdlib.h>
+
+#include "vnd_objective.cuh"
 
 namespace vnd {
 
-constexpr int OBJ_SLOTS = 12;  // doubles per (clip, candidate) partial, see vnd_b200.h
-#ifndef VND_OBJ_NT
-#define VND_OBJ_NT 640  // 20 warps: measured best of 512 / 640 / 768 / 896 / 1024 threads (16 frames per lane)
-#endif
-constexpr int OBJ_NT = VND_OBJ_NT;
-#ifndef VND_OBJ_R
-#define VND_OBJ_R 16
-#endif
-constexpr int OBJ_R = VND_OBJ_R;  // frames per lane and pass (even: the taps are applied with packed adds)
-constexpr int OBJ_TILE = 4096;
-
-struct ObjParams {
-  const float* clips;
-  long long frames, clip_stride, chan_stride;
-  const int* words;
-  const int* offsets;
-  int n_cand;
-  int apply_gain;
-  int halo;
-  int cand_per_group;
-  int tiles_per_chunk;
-  int n_chunks;
-  double* chunk_partials;  // [clip][chunk][cand][OBJ_SLOTS]
-};
-
-// atan(t) for t in [0, 1]: t * P(t^2), |error| <= 1e-7 (degree-8 minimax fit, float32 Horner).
-__device__ __forceinline__ float atan01(float t) {
-  const float z = t * t;
-  float p = 0.00245671847107214f;
-  p = fmaf(p, z, -0.01440133168500584f);
-  p = fmaf(p, z, 0.03978117728736144f);
-  p = fmaf(p, z, -0.07234853052703884f);
-  p = fmaf(p, z, 0.10498943808759016f);
-  p = fmaf(p, z, -0.14161228535203682f);
-  p = fmaf(p, z, 0.19985906672823953f);
-  p = fmaf(p, z, -0.3333259702410447f);
-  p = fmaf(p, z, 0.9999998863844667f);
-  return p * t;
-}
-
-// Packed fp32 arithmetic (sm_100+): two IEEE round-to-nearest operations per instruction on an aligned
-// register pair (FADD2 / FMUL2 / FFMA2 in SASS): same bits as two scalar operations, half the issue slots.
-typedef unsigned long long obj_pair_t;
-#define VND_OBJ_PACKED(name, op)                                                   \
-  __device__ __forceinline__ void name(float& a0, float& a1, float b0, float b1) { \
-    obj_pair_t ra, rb;                                                             \
-    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));                   \
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));                   \
-    asm(op ".rn.f32x2 %0, %0, %1;" : "+l"(ra) : "l"(rb));                         \
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(ra));                  \
-  }
-VND_OBJ_PACKED(obj_add2, "add")
-VND_OBJ_PACKED(obj_sub2, "sub")
-VND_OBJ_PACKED(obj_mul2, "mul")
-// (a0, a1) = (a0, a1) * (b0, b1) + (c0, c1), one rounding each (FFMA2)
-__device__ __forceinline__ void obj_fma2(float& a0, float& a1, float b0, float b1, float c0, float c1) {
-  obj_pair_t ra, rb, rc;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c0), "f"(c1));
-  asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(ra) : "l"(rb), "l"(rc));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(ra));
-}
-
-// Ratio tracker: record (ad, as) when ad / as > bd / bs, i.e. when ad * bs > bd * as, decided EXACTLY: the product of
-// two float32 values is exact in float64 and cannot underflow there.  The float32 pre-test only filters frames that
-// are certainly below the record: rounding is monotone, so exact(ad * bs) > exact(bd * as) implies
-// fl(ad * bs) >= fl(bd * as) >= fl(fl(bd * as) * 0.99999f), and underflowed (zero) products pass the test too.
-// Records are rare (a logarithmic number per lane), so the float64 compare is almost never executed.
-__device__ __forceinline__ void track_ratio(float ad, float as, float& bd, float& bs) {
-  if (ad * bs >= (bd * as) * 0.99999f) {
-    if ((double)ad * (double)bs > (double)bd * (double)as) {  // ties keep the earlier frame
-      bd = ad;
-      bs = as;
-    }
-  }
-}
-
-struct LaneAcc {
-  float sr, srt, srt2, srt3, slr, sll;
-  float d_pos, s_pos, d_neg, s_neg;  // |d|, |s| of the frame with the largest |d|/|s| per sign of s
-};
-
-__device__ __forceinline__ void lane_acc_frame(LaneAcc& a, float l, float r_) {
-  const float d = fsub(l, r_), s = fadd(l, r_);  // utils/dsp.py:399-401
-  const float ad = fabsf(d), as = fabsf(s);
-  const float mx = fmaxf(ad, as), mn = fminf(ad, as);
-  const float t = mx > 0.0f ? __fdividef(mn, mx) : 0.0f;
-  float th = atan01(t);
-  if (ad > as) th = 1.57079632679489662f - th;
-  th = __int_as_float(__float_as_int(th) | ((__float_as_int(d) ^ __float_as_int(s)) & 0x80000000));
-  const float rad = __fsqrt_rn(fadd(fmul(l, l), fmul(r_, r_)));  // utils/dsp.py:413
-  const float rt = rad * th;
-  a.sr += rad;
-  a.srt += rt;
-  a.srt2 = fmaf(rt, th, a.srt2);
-  a.srt3 = fmaf(rt * th, th, a.srt3);
-  a.slr = fmaf(l, r_, a.slr);
-  a.sll = fmaf(l, l, a.sll);
-  if (s >= 0.0f) track_ratio(ad, as, a.d_pos, a.s_pos);
-  else track_ratio(ad, as, a.d_neg, a.s_neg);
-}
-
-// Two frames at once with packed arithmetic.  The amplitude-weighted sums run in two interleaved
-// chains per lane (even / odd frames, slot [0] / [1]), added together before the warp reduction; the
-// ratio trackers stay scalar and see the frames in order.
-struct LaneAcc2 {
-  float sr[2], srt[2], srt2[2], srt3[2], slr[2], sll[2];
-  float d_pos, s_pos, d_neg, s_neg;
-};
-
-__device__ __forceinline__ float obj_theta(float t, float p, float ad, float as, float d, float s) {
-  float th = p * t;
-  if (ad > as) th = 1.57079632679489662f - th;
-  return __int_as_float(__float_as_int(th) | ((__float_as_int(d) ^ __float_as_int(s)) & 0x80000000));
-}
-
-__device__ __forceinline__ void lane_acc_pair(LaneAcc2& a, float l0, float l1, float r0, float r1) {
-  float d0 = l0, d1 = l1, s0 = l0, s1 = l1;
-  obj_sub2(d0, d1, r0, r1);  // utils/dsp.py:399-401
-  obj_add2(s0, s1, r0, r1);
-  const float ad0 = fabsf(d0), as0 = fabsf(s0), ad1 = fabsf(d1), as1 = fabsf(s1);
-  const float mx0 = fmaxf(ad0, as0), mn0 = fminf(ad0, as0), mx1 = fmaxf(ad1, as1), mn1 = fminf(ad1, as1);
-  const float t0 = mx0 > 0.0f ? __fdividef(mn0, mx0) : 0.0f, t1 = mx1 > 0.0f ? __fdividef(mn1, mx1) : 0.0f;
-  float z0 = t0, z1 = t1;
-  obj_mul2(z0, z1, t0, t1);
-  float p0 = 0.00245671847107214f, p1 = p0;  // atan01's polynomial on both frames
-  obj_fma2(p0, p1, z0, z1, -0.01440133168500584f, -0.01440133168500584f);
-  obj_fma2(p0, p1, z0, z1, 0.03978117728736144f, 0.03978117728736144f);
-  obj_fma2(p0, p1, z0, z1, -0.07234853052703884f, -0.07234853052703884f);
-  obj_fma2(p0, p1, z0, z1, 0.10498943808759016f, 0.10498943808759016f);
-  obj_fma2(p0, p1, z0, z1, -0.14161228535203682f, -0.14161228535203682f);
-  obj_fma2(p0, p1, z0, z1, 0.19985906672823953f, 0.19985906672823953f);
-  obj_fma2(p0, p1, z0, z1, -0.3333259702410447f, -0.3333259702410447f);
-  obj_fma2(p0, p1, z0, z1, 0.9999998863844667f, 0.9999998863844667f);
-  const float th0 = obj_theta(t0, p0, ad0, as0, d0, s0), th1 = obj_theta(t1, p1, ad1, as1, d1, s1);
-  float q0 = l0, q1 = l1, w0 = r0, w1 = r1;  // utils/dsp.py:413: sqrt(l*l + r*r), products rounded separately
-  obj_mul2(q0, q1, l0, l1);
-  obj_mul2(w0, w1, r0, r1);
-  obj_add2(q0, q1, w0, w1);
-  const float rad0 = __fsqrt_rn(q0), rad1 = __fsqrt_rn(q1);
-  float rt0 = rad0, rt1 = rad1;
-  obj_mul2(rt0, rt1, th0, th1);
-  obj_add2(a.sr[0], a.sr[1], rad0, rad1);
-  obj_add2(a.srt[0], a.srt[1], rt0, rt1);
-  float u0 = rt0, u1 = rt1;
-  obj_fma2(u0, u1, th0, th1, a.srt2[0], a.srt2[1]);
-  a.srt2[0] = u0;
-  a.srt2[1] = u1;
-  obj_mul2(rt0, rt1, th0, th1);
-  obj_fma2(rt0, rt1, th0, th1, a.srt3[0], a.srt3[1]);
-  a.srt3[0] = rt0;
-  a.srt3[1] = rt1;
-  float v0 = l0, v1 = l1;
-  obj_fma2(v0, v1, r0, r1, a.slr[0], a.slr[1]);
-  a.slr[0] = v0;
-  a.slr[1] = v1;
-  v0 = l0;
-  v1 = l1;
-  obj_fma2(v0, v1, l0, l1, a.sll[0], a.sll[1]);
-  a.sll[0] = v0;
-  a.sll[1] = v1;
-  if (s0 >= 0.0f) track_ratio(ad0, as0, a.d_pos, a.s_pos);
-  else track_ratio(ad0, as0, a.d_neg, a.s_neg);
-  if (s1 >= 0.0f) track_ratio(ad1, as1, a.d_pos, a.s_pos);
-  else track_ratio(ad1, as1, a.d_neg, a.s_neg);
-}
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// best ratio across the warp: every lane ends with the same (d, s)
-__device__ __forceinline__ void warp_best_ratio(float& d, float& s) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float od = __shfl_xor_sync(0xffffffffu, d, o);
-    const float os = __shfl_xor_sync(0xffffffffu, s, o);
-    const double lhs = (double)od * (double)s, rhs = (double)d * (double)os;  // exact products
-    if (lhs > rhs || (lhs == rhs && od > d)) { d = od; s = os; }
-  }
-}
+size_t objective_tmem_workspace_bytes(long long frames, int n_clips, int n_cand, int sm_count);
+int vn_objective_tmem_launch(const float* clips, long long frames, int n_clips, long long clip_stride, long long chan_stride,
+                             const vnd_tap_program* cand, double* partials, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 template <int R>
 __device__ __forceinline__ void run_candidate(const float* __restrict__ px, const int* __restrict__ prog, int apply_gain, float (&yv)[R]) {
@@ -355,7 +176,7 @@ __global__ void __launch_bounds__(OBJ_NT, VND_OBJ_MINB) vn_objective_kernel(cons
       __syncwarp();
       LaneAcc a{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 1.f};
       if (nvalid == OBJ_TILE) {  // whole tile: no bounds checks, frames in packed pairs
-        LaneAcc2 b{{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, 0.f, 1.f, 0.f, 1.f};
+        LaneAcc2 b{{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, 0.f, 1.f, 0.f, 1.f, -1.f, -1.f};
         for (int base = 0; base < OBJ_TILE; base += 32 * OBJ_R) {
           float yv[OBJ_R];
           run_candidate_v4<OBJ_R>(s0 + base + 4 * lane, myprog, mydec, p.apply_gain, yv);
@@ -437,6 +258,12 @@ __global__ void obj_combine_kernel(const double* __restrict__ chunk_partials, do
   for (int k = 0; k < OBJ_SLOTS; ++k) o[k] = r[k];
 }
 
+int obj_combine_launch(const double* chunk_partials, double* partials, int n_clips, int n_chunks, int n_cand, cudaStream_t st) {
+  const long long pairs = (long long)n_clips * n_cand;
+  obj_combine_kernel<<<(unsigned)ceil_div<long long>(pairs, 128), 128, 0, st>>>(chunk_partials, partials, n_clips, n_chunks, n_cand);
+  return after_launch("obj_combine_kernel");
+}
+
 // ------------------------------------------------------------------------------------------------
 // Haas candidates: float64 throughout (optimization.py:183-203 builds LR-mode HaasEffects whose
 // output is float64).  One CTA per (clip, candidate); 8 doubles per pair:
@@ -504,6 +331,17 @@ __global__ void __launch_bounds__(256) haas_objective_kernel(const TIn* __restri
 // ------------------------------------------------------------------------------------------------
 // launch planning
 // ------------------------------------------------------------------------------------------------
+// The tensor-memory variant (vnd_objective_tmem.cu) is opt-in (VND_OBJ_TMEM=1): measured on 16 clips x 1024 strengths
+// x 30 s it reaches 81 k evaluations/s against 136 k for the kernel below.  ncu (profiles/r02_summary.md): ~93 of the
+// ~116 instructions per frame-evaluation are the polar moments, not the taps, so taking the taps off the shared-memory
+// pipe (70 % busy here) buys little, while the 32-outputs-per-lane layout of the TMEM rows needs 163 registers: 12 warps
+// per SM instead of 20 to hide the moments' dependent chains (issue 44 % instead of 63 %).
+static bool obj_tmem_disabled() {
+  const char* e = getenv("VND_OBJ_TMEM");
+  return !(e && e[0] == '1');
+}
+#define g_obj_disable_tmem obj_tmem_disabled()
+
 struct ObjPlan {
   int cand_per_group, n_groups, tiles_per_chunk, n_chunks;
   size_t smem;
@@ -551,6 +389,10 @@ static int plan_objective(long long frames, int n_clips, int n_cand, int halo, i
     }
   }
   int tpc = (int)ceil_div<long long>(tiles, n_chunks);
+  if (const char* e = getenv("VND_OBJ_TPC")) {  // tuning: force the tiles per chunk (clamped to what the workspace was sized for)
+    const int v = atoi(e);
+    if (v > 0 && ceil_div<long long>(tiles, v) <= cap) tpc = v;
+  }
   n_chunks = ceil_div<long long>(tiles, tpc);
   pl->cand_per_group = cpg;
   pl->n_groups = ceil_div(n_cand, cpg);
@@ -569,6 +411,8 @@ int objective_workspace_bytes(long long frames, int n_clips, int n_cand, size_t*
   const long long tiles = ceil_div<long long>(frames, OBJ_TILE);
   const long long chunks = max_chunks(tiles, n_clips, di.sm_count);
   *bytes = (size_t)n_clips * chunks * n_cand * OBJ_SLOTS * 8 + 256;
+  const size_t tm_bytes = objective_tmem_workspace_bytes(frames, n_clips, n_cand, di.sm_count);  // the tensor-memory kernel tiles finer
+  if (tm_bytes > *bytes) *bytes = tm_bytes;
   return VND_OK;
 }
 
@@ -577,6 +421,10 @@ int vn_objective_launch(const float* clips, long long frames, int n_clips, long 
   if (n_clips == 0 || cand->channels == 0) return VND_OK;
   // the reference takes max(|theta|) of the frames: an empty signal is a ValueError there (optimization.py:41-43)
   VND_REQUIRE(frames > 0, VND_EINVAL, "objective of an empty signal (zero-size array to reduction operation maximum which has no identity)");
+  if (!g_obj_disable_tmem) {  // taps through tensor memory whenever the family fits (vnd_objective_tmem.cu)
+    const int rc_tm = vn_objective_tmem_launch(clips, frames, n_clips, clip_stride, chan_stride, cand, partials, workspace, workspace_bytes, st);
+    if (rc_tm != VND_EUNSUPPORTED) return rc_tm;
+  }
   int halo = cand->halo > 0 ? cand->halo : 0;
   if (halo > frames) halo = (int)frames;
   halo = (halo + 3) & ~3;
@@ -608,10 +456,7 @@ int vn_objective_launch(const float* clips, long long frames, int n_clips, long 
   vn_objective_kernel<<<grid, OBJ_NT, pl.smem, st>>>(p, mpw);
   rc = after_launch("vn_objective_kernel");
   if (rc) return rc;
-  const long long pairs = (long long)n_clips * cand->channels;
-  obj_combine_kernel<<<(unsigned)ceil_div<long long>(pairs, 128), 128, 0, st>>>(p.chunk_partials, partials, n_clips, pl.n_chunks,
-                                                                                 cand->channels);
-  return after_launch("obj_combine_kernel");
+  return obj_combine_launch(p.chunk_partials, partials, n_clips, pl.n_chunks, cand->channels, st);
 }
 
 int haas_objective_launch(const void* clips, int clip_dtype, long long frames, int n_clips, long long clip_stride, long long chan_stride,

@@ -335,6 +335,32 @@ def optimize_local_minima(local_minima: list[int], scalars, grid_size: int, scal
     return best_scalar
 
 
+# ------------------------------------------------------------------------------------------------
+# The two functions below (``_bounded_brent`` and, in array form, ``_BrentBatch``) restate
+# ``scipy.optimize._optimize._minimize_scalar_bounded`` statement for statement, which SURVEY.md section 8(f).1 asks for so
+# that every comparison of the refinement comes out as in the reference.  That routine is part of SciPy:
+#
+#   Copyright (c) 2001-2002 Enthought, Inc. 2003, SciPy Developers.  All rights reserved.
+#
+#   Redistribution and use in source and binary forms, with or without modification, are permitted provided that the
+#   following conditions are met:
+#   1. Redistributions of source code must retain the above copyright notice, this list of conditions and the following
+#      disclaimer.
+#   2. Redistributions in binary form must reproduce the above copyright notice, this list of conditions and the
+#      following disclaimer in the documentation and/or other materials provided with the distribution.
+#   3. Neither the name of the copyright holder nor the names of its contributors may be used to endorse or promote
+#      products derived from this software without specific prior written permission.
+#
+#   THIS SOFTWARE IS PROVIDED BY THE COPYRIGHT HOLDERS AND CONTRIBUTORS "AS IS" AND ANY EXPRESS OR IMPLIED WARRANTIES,
+#   INCLUDING, BUT NOT LIMITED TO, THE IMPLIED WARRANTIES OF MERCHANTABILITY AND FITNESS FOR A PARTICULAR PURPOSE ARE
+#   DISCLAIMED. IN NO EVENT SHALL THE COPYRIGHT OWNER OR CONTRIBUTORS BE LIABLE FOR ANY DIRECT, INDIRECT, INCIDENTAL,
+#   SPECIAL, EXEMPLARY, OR CONSEQUENTIAL DAMAGES (INCLUDING, BUT NOT LIMITED TO, PROCUREMENT OF SUBSTITUTE GOODS OR
+#   SERVICES; LOSS OF USE, DATA, OR PROFITS; OR BUSINESS INTERRUPTION) HOWEVER CAUSED AND ON ANY THEORY OF LIABILITY,
+#   WHETHER IN CONTRACT, STRICT LIABILITY, OR TORT (INCLUDING NEGLIGENCE OR OTHERWISE) ARISING IN ANY WAY OUT OF THE USE
+#   OF THIS SOFTWARE, EVEN IF ADVISED OF THE POSSIBILITY OF SUCH DAMAGE.
+#
+# (BSD 3-Clause; the algorithm is Forsythe, Malcolm and Moler's ``fmin``.)
+# ------------------------------------------------------------------------------------------------
 def _bounded_brent(x1, x2, xatol: float, maxiter: int = 500):
     """Brent's bounded scalar minimiser as a coroutine: yields the next abscissa, is sent the function value, and
     returns an ``OptimizeResult`` when it has converged.
@@ -462,17 +488,172 @@ def lockstep_minimize(bounds: Sequence[tuple[float, float]], batch_objective: Ca
     return results
 
 
+class _BrentBatch:
+    """``_bounded_brent`` for MANY intervals at once, as array arithmetic: one state vector per variable of scipy's
+    ``_minimize_scalar_bounded``, every statement of its loop applied under a mask to the minimisers that take it.
+
+    The element-wise operations (+, -, *, /, abs, sign, comparisons, maximum) are IEEE basic operations, identical in
+    an array and on scalars, and the dtypes are the scalar code's: abscissae and step sizes float64, function values
+    the objective's own dtype (float32 for velvet-noise candidates), so that ``(xf - nfc) * (fx - ffulc)`` is a float64
+    product of a float64 and an exactly widened float32 difference, as under numpy's scalar promotion.  Every minimiser
+    therefore sees the abscissae, takes the branches and returns the values of the coroutine (and so of scipy);
+    ``tests/test_host_logic.py`` compares them abscissa by abscissa on thousands of float32 objectives.  A Brent round
+    over 20 000 minimisers costs about a millisecond here instead of 0.1 s of Python generator switches."""
+
+    def __init__(self, lows, highs, xatol: float, maxiter: int = 500):
+        from math import sqrt
+
+        a = np.asarray(lows, dtype=np.float64).copy()
+        b = np.asarray(highs, dtype=np.float64).copy()
+        if not (np.all(np.isfinite(a)) and np.all(np.isfinite(b))):
+            raise ValueError("Optimization bounds must be finite scalars.")
+        if np.any(a > b):
+            raise ValueError("The lower bound exceeds the upper bound.")
+        self.n = len(a)
+        self.xatol, self.maxiter = xatol, maxiter
+        self.sqrt_eps = sqrt(2.2e-16)
+        self.golden_mean = 0.5 * (3.0 - sqrt(5.0))
+        self.a, self.b = a, b
+        self.fulc = a + self.golden_mean * (b - a)
+        self.nfc = self.fulc.copy()
+        self.xf = self.fulc.copy()
+        self.rat = np.zeros(self.n)
+        self.e = np.zeros(self.n)
+        self.x = self.xf.copy()
+        self.num = np.zeros(self.n, dtype=np.int64)
+        self.flag = np.zeros(self.n, dtype=np.int64)
+        self.live = np.ones(self.n, dtype=bool)
+        self.started = False
+        self.fx = self.ffulc = self.fnfc = self.fu = None
+
+    def pending(self):
+        """Indices of the live minimisers and the abscissa each wants evaluated."""
+        idx = np.nonzero(self.live)[0]
+        return idx, self.x[idx]
+
+    def _propose(self, m):
+        """The body of scipy's ``while`` loop up to the evaluation, for the minimisers in mask ``m`` (all of which
+        passed the loop condition)."""
+        a, b, xf, nfc, fulc, fx, ffulc, fnfc, xm, tol1, tol2 = (self.a, self.b, self.xf, self.nfc, self.fulc, self.fx, self.ffulc, self.fnfc, self.xm,
+                                                                self.tol1, self.tol2)
+        golden = m.copy()
+        para = m & (np.abs(self.e) > tol1)
+        if para.any():
+            i = np.nonzero(para)[0]
+            r = (xf[i] - nfc[i]) * (fx[i] - ffulc[i])
+            q = (xf[i] - fulc[i]) * (fx[i] - fnfc[i])
+            p = (xf[i] - fulc[i]) * q - (xf[i] - nfc[i]) * r
+            q = 2.0 * (q - r)
+            p = np.where(q > 0.0, -p, p)
+            q = np.abs(q)
+            r = self.e[i]
+            self.e[i] = self.rat[i]
+            ok = (np.abs(p) < np.abs(0.5 * q * r)) & (p > q * (a[i] - xf[i])) & (p < q * (b[i] - xf[i]))
+            golden[i] = ~ok
+            if ok.any():
+                j = i[ok]
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    rat = (p[ok] + 0.0) / q[ok]
+                x = xf[j] + rat
+                near = ((x - a[j]) < tol2[j]) | ((b[j] - x) < tol2[j])
+                d = xm[j] - xf[j]
+                si = np.sign(d) + (d == 0)
+                self.rat[j] = np.where(near, tol1[j] * si, rat)
+        if golden.any():
+            i = np.nonzero(golden)[0]
+            self.e[i] = np.where(xf[i] >= xm[i], a[i] - xf[i], b[i] - xf[i])
+            self.rat[i] = self.golden_mean * self.e[i]
+        i = np.nonzero(m)[0]
+        si = np.sign(self.rat[i]) + (self.rat[i] == 0)
+        self.x[i] = xf[i] + si * np.maximum(np.abs(self.rat[i]), tol1[i])
+
+    def _close_or_propose(self, m):
+        """Loop condition for the minimisers in ``m``: the converged ones finish, the others get their next abscissa."""
+        go = m & (np.abs(self.xf - self.xm) > (self.tol2 - 0.5 * (self.b - self.a)))
+        self.live[m & ~go] = False
+        if go.any():
+            self._propose(go)
+
+    def feed(self, idx, values):
+        """Function values (array in the objective's dtype) for the abscissae handed out by ``pending``."""
+        values = np.asarray(values)
+        if not self.started:  # the first evaluation of every minimiser (scipy evaluates before its loop)
+            assert len(idx) == self.n
+            self.started = True
+            self.fx = values.copy()
+            self.ffulc = values.copy()
+            self.fnfc = values.copy()
+            self.fu = np.full(self.n, np.inf, dtype=values.dtype)
+            self.num[:] = 1
+            self.xm = 0.5 * (self.a + self.b)
+            self.tol1 = self.sqrt_eps * np.abs(self.xf) + self.xatol / 3.0
+            self.tol2 = 2.0 * self.tol1
+            self._close_or_propose(self.live.copy())
+            return
+        a, b, x, xf = self.a, self.b, self.x, self.xf
+        fu = values
+        self.fu[idx] = fu
+        self.num[idx] += 1
+        better = fu <= self.fx[idx]
+        ib, iw = idx[better], idx[~better]
+        if len(ib):  # fu <= fx
+            right = x[ib] >= xf[ib]
+            a[ib[right]] = xf[ib[right]]
+            b[ib[~right]] = xf[ib[~right]]
+            self.fulc[ib], self.ffulc[ib] = self.nfc[ib], self.fnfc[ib]
+            self.nfc[ib], self.fnfc[ib] = xf[ib], self.fx[ib]
+            self.xf[ib], self.fx[ib] = x[ib], fu[better]
+        if len(iw):
+            fw = fu[~better]
+            left = x[iw] < xf[iw]
+            a[iw[left]] = x[iw[left]]
+            b[iw[~left]] = x[iw[~left]]
+            c1 = (fw <= self.fnfc[iw]) | (self.nfc[iw] == xf[iw])
+            c2 = ~c1 & ((fw <= self.ffulc[iw]) | (self.fulc[iw] == xf[iw]) | (self.fulc[iw] == self.nfc[iw]))
+            i1, i2 = iw[c1], iw[c2]
+            self.fulc[i1], self.ffulc[i1] = self.nfc[i1], self.fnfc[i1]
+            self.nfc[i1], self.fnfc[i1] = x[i1], fw[c1]
+            self.fulc[i2], self.ffulc[i2] = x[i2], fw[c2]
+        self.xm[idx] = 0.5 * (a[idx] + b[idx])
+        self.tol1[idx] = self.sqrt_eps * np.abs(self.xf[idx]) + self.xatol / 3.0
+        self.tol2[idx] = 2.0 * self.tol1[idx]
+        m = np.zeros(self.n, dtype=bool)
+        m[idx] = True
+        over = m & (self.num >= self.maxiter)
+        self.flag[over] = 1
+        self.live[over] = False
+        self._close_or_propose(m & ~over)
+
+    def results(self):
+        """(x, fun, nfev) arrays; ``fun`` in the objective's dtype, like ``OptimizeResult.fun``."""
+        return self.xf.copy(), self.fx.copy(), self.num.copy()
+
+
+def lockstep_minimize_arrays(lows, highs, batch_objective: Callable[..., Any], *, xatol: float = 1e-4):
+    """``lockstep_minimize`` on the array engine: ``batch_objective(abscissae, ids)`` (numpy arrays) returns the values
+    as an array in the objective's dtype.  Returns ``(x, fun, nfev)`` arrays in input order."""
+    eng = _BrentBatch(lows, highs, xatol)
+    while True:
+        idx, xs = eng.pending()
+        if len(idx) == 0:
+            break
+        eng.feed(idx, batch_objective(xs, idx))
+    return eng.results()
+
+
 def optimize_local_minima_batched(local_minima: list[int], scalars, grid_size: int, batch_objective: Callable[[list[float]], Sequence[Any]]):
     """``optimize_local_minima`` with all minima refined in lock-step (one launch per Brent iteration
     instead of one per evaluation); same bounds, same ``xatol``, same first-strictly-best rule
-    (optimization.py:131-155)."""
+    (optimization.py:131-155).  ``batch_objective(list of abscissae)`` returns their values."""
     print("Starting Local Minima optimization")
-    bounds = [(scalars[max(0, i - 1)], scalars[min(grid_size - 1, i + 1)]) for i in local_minima]
+    lows = [scalars[max(0, i - 1)] for i in local_minima]
+    highs = [scalars[min(grid_size - 1, i + 1)] for i in local_minima]
+    xs, funs, _ = lockstep_minimize_arrays(lows, highs, lambda x, ids: np.asarray(batch_objective([float(v) for v in x])), xatol=1e-4)
     best_scalar, best_score = 0.0, np.inf
-    for result in lockstep_minimize(bounds, batch_objective, xatol=1e-4):
-        if result.fun < best_score:
-            best_score = result.fun
-            best_scalar = result.x
+    for x, fun in zip(xs, funs):
+        if fun < best_score:
+            best_score = fun
+            best_scalar = x
     return best_scalar
 
 
@@ -703,31 +884,26 @@ def optimize_velvet_noise_batch(*, input_signals=None, sample_rate_hz: int, dura
     best = np.zeros(hi - lo, dtype=np.float64)
     if hi > lo:
         print("Starting Local Minima optimization")
-        bounds, owner = [], []
+        lows, highs, owner = [], [], []
         for ci in range(lo, hi):
             for i in minima[ci]:
-                bounds.append((kappas[max(0, i - 1)], kappas[min(grid_size - 1, i + 1)]))
+                lows.append(kappas[max(0, i - 1)])
+                highs.append(kappas[min(grid_size - 1, i + 1)])
                 owner.append(ci - lo)
+        owner = np.asarray(owner, dtype=np.int64)
 
-        def batch(xs, ids):
-            req: list[list[float]] = [[] for _ in range(hi - lo)]
-            for x, j in zip(xs, ids):
-                req[owner[j]].append(x)
-            vals = bank.scores(req)
-            pos = [0] * (hi - lo)
-            out = []
-            for j in ids:
-                c = owner[j]
-                out.append(vals[c][pos[c]])
-                pos[c] += 1
-            return out
+        def batch(xs, ids):  # ids ascend and the minimisers are listed clip by clip: a clip's requests are one contiguous run
+            own = owner[ids]
+            cuts = np.searchsorted(own, np.arange(hi - lo + 1))
+            vals = bank.scores([xs[cuts[c]: cuts[c + 1]] for c in range(hi - lo)])
+            return np.concatenate(vals) if len(vals) else np.zeros(0, dtype=np.float32)
 
-        results = lockstep_minimize(bounds, batch, xatol=1e-4, with_ids=True)
+        xs, funs, _ = lockstep_minimize_arrays(lows, highs, batch, xatol=1e-4)
         best_score = [np.inf] * (hi - lo)
-        for res, c in zip(results, owner):  # first strictly best minimum of each clip (optimization.py:150-153)
-            if res.fun < best_score[c]:
-                best_score[c] = res.fun
-                best[c] = res.x
+        for x, fun, c in zip(xs, funs, owner):  # first strictly best minimum of each clip (optimization.py:150-153)
+            if fun < best_score[c]:
+                best_score[c] = fun
+                best[c] = x
     refined = S.all_gather_rows(best.reshape(-1, 1), counts, device=device, group=group).reshape(-1)
     if details:
         info = {"scores": scores, "local_minima": minima, "argmin": [int(np.argmin(r)) for r in scores],

@@ -1,10 +1,10 @@
 """Stereo helpers of the hot path, with the reference's names and in-place contracts
 (``src/vndecorrelate/utils/dsp.py``), executed by the CUDA library.
 
-Only what ``VelvetNoise.decorrelate`` / ``HaasEffect`` / the optimiser touch is here: the M/S
-helpers, width, side-channel encode, RMS normalisation, the dtype/shape helpers and the tap-position
-maths.  Analysis and plotting helpers of the reference (``cross_correlogram``, ``sine_sweep``,
-``peak_normalize`` …) are outside the hot path and are not provided.
+What ``VelvetNoise.decorrelate`` / ``HaasEffect`` / the optimiser touch is here: the M/S helpers, width,
+side-channel encode, the normalisers (``rms_normalize`` in every mode, ``peak_normalize``), ``polar_coordinates``,
+the dtype/shape helpers and the tap-position maths.  The reference's remaining analysis and plotting helpers
+(``cross_correlogram``, ``sine_sweep``, envelopes) are outside the hot path and are not provided.
 
 All in-place functions take numpy arrays (float32 or float64, shape ``(n, 2)``) or CUDA
 ``torch.Tensor``s and return ``None`` like the reference's.
@@ -26,7 +26,7 @@ EPSILON: float = 1e-10  # utils/dsp.py:6
 __all__ = [
     "EPSILON", "IDENTITY_ENVELOPE", "NormalizeMode", "LayoutMode", "apply_stereo_width",
     "encode_signal_to_side_channel", "to_float32", "rms_normalize", "mono_to_stereo", "stereo_to_mono",
-    "LR_to_MS", "MS_to_LR", "generate_log_distribution", "apply_log_distribution", "uniform_density",
+    "LR_to_MS", "MS_to_LR", "generate_log_distribution", "apply_log_distribution", "uniform_density", "peak_normalize", "polar_coordinates",
     "check_mono", "check_stereo", "check_equal_length",
 ]
 
@@ -151,18 +151,133 @@ def encode_signal_to_side_channel(input_signal, decorrelated_signal) -> None:
     _stereo_op(decorrelated_signal, _OP_ENCODE, dry=input_signal)
 
 
-def rms_normalize(input_signal, output_signal, mode: NormalizeMode = NormalizeMode.DUAL_MONO, epsilon: float = EPSILON) -> None:
-    """Scale each channel of ``output_signal`` in place to the RMS of the same channel of
-    ``input_signal`` (utils/dsp.py:87-109), reproducing numpy's sequential axis-0 summation.
+def _flat_inplace(fn_host, fn_dev, arrays, make_args):
+    """Run an in-place device helper on contiguous views of ``arrays`` (numpy: upload / run / download inside the host
+    call; CUDA tensors: on torch's stream), copying back when a contiguous temporary had to be made."""
+    first = arrays[-1]
+    if R.is_torch_tensor(first):
+        import torch
 
-    Only the DUAL_MONO mode on ``(n, 2)`` signals — what ``VelvetNoise`` uses — is on the hot
-    path; STEREO mode, 1-D signals and a non-default epsilon are not provided."""
-    if mode != NormalizeMode.DUAL_MONO or input_signal.ndim != 2 or output_signal.ndim != 2 or epsilon != EPSILON:
-        raise NotImplementedError("only rms_normalize(x, y) in DUAL_MONO mode on 2-D signals is part of the accelerated hot path")
-    check_stereo(input_signal)
-    check_stereo(output_signal)
-    check_equal_length(input_signal, output_signal)
-    _stereo_op(output_signal, _OP_RMS, dry=input_signal)
+        work = [a if a.is_contiguous() else a.contiguous() for a in arrays]
+        nbytes = C.c_size_t()
+        N.check(N.lib().vnd_dsp_workspace(max(int(w.numel()) for w in work), C.byref(nbytes)), "vnd_dsp_workspace")
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=first.device)
+        with torch.cuda.device(first.device):
+            fn_dev(work, ws.data_ptr(), nbytes.value, R.torch_stream_ptr(first))
+        if work[-1] is not arrays[-1]:
+            arrays[-1].copy_(work[-1])
+        return
+    work = [a if a.flags.c_contiguous else np.ascontiguousarray(a) for a in arrays]
+    if not work[-1].flags.writeable:
+        raise ValueError("output array is read-only")
+    fn_host(work)
+    if work[-1] is not arrays[-1]:
+        arrays[-1][...] = work[-1]
+
+
+def _sig(a):
+    return R.torch_signal(a) if R.is_torch_tensor(a) else R.host_signal(a)
+
+
+def rms_normalize(input_signal, output_signal, mode: NormalizeMode = NormalizeMode.DUAL_MONO, epsilon: float = EPSILON) -> None:
+    """Scale ``output_signal`` in place to the RMS of ``input_signal`` (utils/dsp.py:87-109).
+
+    DUAL_MONO on 2-D signals - what ``VelvetNoise`` uses - gives every channel its own gain from numpy's sequential
+    axis-0 sums; STEREO mode and 1-D signals use one gain from statistics over the whole array, summed in numpy's
+    pairwise order.  Both orders are reproduced bit for bit on the device."""
+    stereo = mode == NormalizeMode.STEREO
+    if input_signal.ndim not in (1, 2) or output_signal.ndim not in (1, 2):
+        raise ValueError(f"Input shape invalid: Expected shape (num samples,) or (num samples, channels), but got shape {tuple(input_signal.shape)}.")
+    in_flat, out_flat = input_signal.ndim == 1 or stereo, output_signal.ndim == 1 or stereo
+    if not in_flat and not out_flat:  # 2-D, DUAL_MONO
+        if epsilon != EPSILON:
+            raise NotImplementedError("rms_normalize in DUAL_MONO mode supports the default epsilon only")
+        check_stereo(input_signal)
+        check_stereo(output_signal)
+        check_equal_length(input_signal, output_signal)
+        _stereo_op(output_signal, _OP_RMS, dry=input_signal)
+        return
+    if in_flat != out_flat:
+        raise NotImplementedError("rms_normalize of a 1-D signal against a 2-D signal in DUAL_MONO mode is not provided")
+    if input_signal.dtype != output_signal.dtype:
+        input_signal = input_signal.to(output_signal.dtype) if R.is_torch_tensor(input_signal) else input_signal.astype(output_signal.dtype)
+    if not R.is_torch_tensor(output_signal):
+        _float_array(output_signal, "signal")
+    lib = N.lib()
+    xn, yn = input_signal.ndim, output_signal.ndim
+
+    def host(w):
+        N.check(lib.vnd_rms_normalize_host(R.HostContext.get().handle, C.byref(_sig(w[0])), xn, C.byref(_sig(w[1])), yn, int(stereo), float(epsilon)),
+                "vnd_rms_normalize_host")
+
+    def dev(w, ws, nbytes, stream):
+        N.check(lib.vnd_rms_normalize_dev(C.byref(_sig(w[0])), xn, C.byref(_sig(w[1])), yn, int(stereo), float(epsilon), ws, nbytes, stream),
+                "vnd_rms_normalize_dev")
+
+    _flat_inplace(host, dev, [input_signal, output_signal], None)
+
+
+def peak_normalize(input_signal, mode: NormalizeMode = NormalizeMode.DUAL_MONO, epsilon: float = EPSILON) -> None:
+    """Scale ``input_signal`` in place to ``[-1, 1]`` by its peak: one peak for 1-D signals and STEREO mode, one per
+    channel in DUAL_MONO mode (utils/dsp.py:71-84)."""
+    stereo = mode == NormalizeMode.STEREO
+    if input_signal.ndim not in (1, 2):
+        raise ValueError(f"Input shape invalid: Expected shape (num samples,) or (num samples, channels), but got shape {tuple(input_signal.shape)}.")
+    if not R.is_torch_tensor(input_signal):
+        _float_array(input_signal, "signal")
+    lib = N.lib()
+    nd = input_signal.ndim
+
+    def host(w):
+        N.check(lib.vnd_peak_normalize_host(R.HostContext.get().handle, C.byref(_sig(w[0])), nd, int(stereo), float(epsilon)), "vnd_peak_normalize_host")
+
+    def dev(w, ws, nbytes, stream):
+        N.check(lib.vnd_peak_normalize_dev(C.byref(_sig(w[0])), nd, int(stereo), float(epsilon), ws, nbytes, stream), "vnd_peak_normalize_dev")
+
+    _flat_inplace(host, dev, [input_signal], None)
+
+
+def polar_coordinates(left, right, mode: LayoutMode = "MS", semicircular: bool = True, normalize: bool = True, compute_weights: bool = True):
+    """Each frame of ``left`` / ``right`` as polar coordinates: ``(radii, thetas, weights)`` or ``(radii, thetas)``
+    (utils/dsp.py:374-422).  ``thetas = arctan2(L - R, L + R)`` in MS mode (``arctan2(L, R)`` otherwise), folded onto
+    ``[-pi/2, pi/2]`` when ``semicircular``; ``radii = sqrt(L^2 + R^2)``, divided by their maximum when ``normalize``;
+    ``weights = radii / (radii.sum() + 1e-10)``.  Radii and weights equal numpy's bit for bit (the sum runs in numpy's
+    pairwise order); the angles are within 2 ulp of numpy's ``arctan2``."""
+    ms = int(mode == LayoutMode.MS)
+    lib = N.lib()
+    if R.is_torch_tensor(left):
+        import torch
+
+        l, r = left.contiguous(), right.to(left.dtype).contiguous()
+        if l.dim() != 1 or l.shape != r.shape or l.dtype not in (torch.float32, torch.float64):
+            raise ValueError("left and right must be 1-D float32/float64 tensors of equal length")
+        n = l.shape[0]
+        rad, th = torch.empty_like(l), torch.empty_like(l)
+        w = torch.empty_like(l) if compute_weights else None
+        nbytes = C.c_size_t()
+        N.check(lib.vnd_dsp_workspace(n, C.byref(nbytes)), "vnd_dsp_workspace")
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=l.device)
+        with torch.cuda.device(l.device):
+            N.check(lib.vnd_polar_dev(l.data_ptr(), r.data_ptr(), n, N.VND_F64 if l.dtype == torch.float64 else N.VND_F32, ms, int(semicircular),
+                                      int(normalize), rad.data_ptr(), th.data_ptr(), w.data_ptr() if w is not None else None, ws.data_ptr(),
+                                      nbytes.value, R.torch_stream_ptr(l)), "vnd_polar_dev")
+        return (rad, th, w) if compute_weights else (rad, th)
+    l = np.asarray(left)
+    r = np.asarray(right)
+    dt = np.result_type(l.dtype, r.dtype)
+    if dt not in (np.float32, np.float64):
+        dt = np.dtype(np.float64) if dt.itemsize > 4 or dt.kind in "iu" and dt.itemsize >= 4 else np.dtype(np.float32)
+    l = np.ascontiguousarray(l, dtype=dt)
+    r = np.ascontiguousarray(r, dtype=dt)
+    if l.ndim != 1 or l.shape != r.shape:
+        raise ValueError(f"operands could not be broadcast together with shapes {l.shape} {r.shape}")
+    n = l.shape[0]
+    rad, th = np.empty(n, dtype=dt), np.empty(n, dtype=dt)
+    w = np.empty(n, dtype=dt) if compute_weights else None
+    N.check(lib.vnd_polar_host(R.HostContext.get().handle, l.ctypes.data, r.ctypes.data, n, N.VND_F64 if dt == np.float64 else N.VND_F32, ms,
+                               int(semicircular), int(normalize), rad.ctypes.data, th.ctypes.data, w.ctypes.data if w is not None else None),
+            "vnd_polar_host")
+    return (rad, th, w) if compute_weights else (rad, th)
 
 
 # ---- tap-position maths (host; utils/dsp.py:170-286) --------------------------------------------
