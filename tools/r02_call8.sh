@@ -1,0 +1,7 @@
+#!/usr/bin/env bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+small="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --channels-per-gpu 16 --frames 2000000 --e2e-channels 2 --configs 4 --cfg4-channels-per-gpu 16 --cfg4-frames 8000000"
+$small > gpurun_out/r02_prof_plain5.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:"fir_tile_kernel.*1024" -s 3 -c 1 -f -o gpurun_out/r02_fir_tile_long $small > gpurun_out/r02_prof_ncu5.log 2>&1; echo "fir_tile long capture rc=$?"; tail -2 gpurun_out/r02_prof_ncu5.log
+STEPS=20 REFARM=1 bash tools/r02_full.sh 2>&1 | tail -22

@@ -110,15 +110,10 @@ struct TmShape {
   static_assert(32 * (kCW * RC + 4 * RH) <= kLaunchRegs * kNT, "register file");
   static_assert(RC % 8 == 0 && RH % 8 == 0, "setmaxnreg takes multiples of 8");
   static_assert(B_COUNT * 8 <= 192, "mbarriers");
-  // Largest tap offset served from TMEM.  Group g could reach RG (G - 1 - g) samples further (its columns start at
-  // offset + RG g), but per-group tap mixes cost more than the saved shared-memory taps: 366 instead of 384 Gsamples/s
-  // on the same box with VND_TM_GROUP_REACH (the three warps of a quarter hand TMEM back together, so the quarter
-  // waits for its slowest group).
-#ifdef VND_TM_GROUP_REACH
-  __host__ __device__ static constexpr int near_max(int g) { return kCols - RG * (g + 1); }
-#else
-  __host__ __device__ static constexpr int near_max(int) { return kCols - kR; }
-#endif
+  // Largest tap offset served from TMEM (every group of a row: group g alone could reach RG (G - 1 - g) samples
+  // further, but per-group tap mixes measured slower - 366 instead of 384 Gsamples/s on the same box - because the
+  // three warps of a quarter hand TMEM back together and the quarter waits for its slowest group).
+  static constexpr int kNearMax = kCols - kR;
 };
 
 struct TmParams {
@@ -137,8 +132,8 @@ struct TmParams {
   int tiles_per_channel;  // interior tiles
 };
 
-// Dynamic shared memory: [0,192) mbarriers | [192,196) TMEM base | [196,212) first all-far segment per group |
-//   [256, ...) float in[NBUF][nblk][pitch] | float stage[128][pitch] | int program[] | int ops[G][] | int4 segtab[G][]
+// Dynamic shared memory: [0,192) mbarriers | [192,196) TMEM base | [196,200) first all-far segment |
+//   [256, ...) float in[NBUF][nblk][pitch] | float stage[128][pitch] | int program[] | int ops[G][] | int4 segtab[]
 // The role functions rebuild their pointers from this symbol so that every access stays in the
 // shared address space (LDS/STS, not generic loads).
 extern __shared__ __align__(128) unsigned char tm_smem[];
@@ -146,12 +141,12 @@ extern __shared__ __align__(128) unsigned char tm_smem[];
 template <class T>
 struct Smem {
   uint64_t* bars;
-  int* s_near_end;  // first segment without a tap in every group's TMEM window
+  int* s_near_end;  // first segment without a tap in the TMEM window
   float* in_all;
   float* stage;
   int* sprog;
   int* ops;  // [G][opstride]: decoded tap operations per thread group
-  int4* segtab;  // [G][opstride / 2]: per segment: taps of the negative and positive list, their leading tensor-memory taps, gain bits
+  int4* segtab;  // per segment: taps of the negative and positive list, their leading tensor-memory taps, gain bits
   int bufw;
   int opstride;
   __device__ __forceinline__ explicit Smem(const TmParams& P) {
@@ -165,11 +160,10 @@ struct Smem {
     ops = sprog + opstride;
     segtab = reinterpret_cast<int4*>(ops + T::kG * opstride);  // opstride is a multiple of 4 words: 16-byte aligned
   }
-  __device__ __forceinline__ const int4* segtab_of(int g) const { return segtab + g * (opstride / 2); }  // 2 * opstride words per group
 };
 template <class T>
 constexpr size_t tm_tail_words(int opstride) {  // program + decoded lists + segment tables
-  return (size_t)(1 + T::kG + 2 * T::kG) * opstride;
+  return (size_t)(3 + T::kG) * opstride;
 }
 
 struct RunInfo {
@@ -202,48 +196,28 @@ __device__ __forceinline__ bool begin_run(const TmParams& P, const Smem<T>& sm, 
   const int S = sm.sprog[0];
   const int* taps = sm.sprog + 1 + 3 * S;
   const int ntaps = r.nprog - 1 - 3 * S;
-  // Segments from near_end on have no tap inside the TMEM window of EVERY group (offsets <= 512 - R): the compute
-  // warps release the quarter's TMEM for the next tile's refill when they reach it, and the refill then runs under
-  // their trailing all-far segments.  Inside the earlier segments a group may serve more taps from TMEM than that:
-  // group g's columns start RG g into the row, so its reach is 512 - RG (g + 1).  (Letting a group keep TMEM taps
-  // in the trailing segments would hold the refill back for the whole quarter.)
-  if (tid == 0) {
+  if (tid == 0) {  // the segment table; segments from near_end on have no tap inside the TMEM window
     const int* tq = taps;
     int ne = 0;
     for (int s = 0; s < S; ++s) {
-      const int n = sm.sprog[1 + 3 * s] + sm.sprog[2 + 3 * s];
-      for (int k = 0; k < n; ++k)
-        if (tq[k] <= kCols - T::kR) ne = s + 1;
-      tq += n;
-    }
-    sm.s_near_end[0] = ne;
-  }
-  __syncthreads();
-  const int near_end = sm.s_near_end[0];
-  if (tid < T::kG) {  // per thread group: the segment table
-    const int g = tid, nmax = T::near_max(g);
-    int4* st = sm.segtab + g * (sm.opstride / 2);
-    const int* tq = taps;
-    for (int s = 0; s < S; ++s) {
       const int n_neg = sm.sprog[1 + 3 * s], n = n_neg + sm.sprog[2 + 3 * s];
+      for (int k = 0; k < n; ++k)
+        if (tq[k] <= T::kNearMax) ne = s + 1;
       int a = 0, b = 0;  // leading tensor-memory taps of the two lists
-      if (s < near_end) {
-        while (a < n_neg && tq[a] <= nmax) ++a;
-        while (n_neg + b < n && tq[n_neg + b] <= nmax) ++b;
-      }
-      st[s] = make_int4(n_neg, n - n_neg, a | (b << 16), p.apply_gain ? sm.sprog[3 + 3 * s] : __float_as_int(1.0f));
+      while (a < n_neg && tq[a] <= T::kNearMax) ++a;
+      while (n_neg + b < n && tq[n_neg + b] <= T::kNearMax) ++b;
+      sm.segtab[s] = make_int4(n_neg, n - n_neg, a | (b << 16), p.apply_gain ? sm.sprog[3 + 3 * s] : __float_as_int(1.0f));
       tq += n;
     }
+    *sm.s_near_end = ne;
   }
   // decode the taps for the thread groups (group g owns outputs RG g .. RG g + RG - 1 of a row)
-  int near_taps = 0;  // taps of the segments before near_end
-  for (int s = 0; s < near_end; ++s) near_taps += sm.sprog[1 + 3 * s] + sm.sprog[2 + 3 * s];
   for (int t = tid; t < T::kG * (ntaps + 2); t += T::kNT) {
     const int g = t / (ntaps + 2), k = t - g * (ntaps + 2);
     int op = 0;  // two slack words behind each list
     if (k < ntaps) {
       const int i = taps[k];
-      if (k < near_taps && i <= T::near_max(g)) {
+      if (i <= T::kNearMax) {
         op = i;
       } else {
         const int o = i + T::kRG * g, A = o & 3, oal = o - A;
@@ -384,7 +358,7 @@ __device__ __noinline__ void compute_main(const TmParams& P, uint32_t tbase, int
   const int m = 32 * q + lane;
   uint64_t* bars = sm.bars;
   const uint32_t tcol0 = tbase + (uint32_t)(RG * g);  // column of this thread's first output
-  const int4* segtab = sm.segtab_of(g);
+  const int4* segtab = sm.segtab;
   int b = 0;           // ring slot of the current tile
   unsigned fpar = 0;   // in_full parity of slot b
   unsigned tpar = 0;   // parity of the tile counter (TMEM and staging barriers)
@@ -393,7 +367,7 @@ __device__ __noinline__ void compute_main(const TmParams& P, uint32_t tbase, int
     if (!begin_run<T>(P, sm, run, tid, r)) continue;
     stagger(q, stagger_ns);
     const int S = sm.sprog[0];
-    const int near_end = sm.s_near_end[0];
+    const int near_end = *sm.s_near_end;
     for (int ti = 0; ti < r.n_tiles; ++ti) {
       const uint32_t row = smem_u32(sm.in_all + b * sm.bufw + m * T::kPitch);
       float yv[RG];
