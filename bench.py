@@ -580,6 +580,20 @@ def run_cfg3(env: Env, args, lib, N, R, VelvetNoise, C):
                "copy_ceiling": {"value": ceiling, "unit": UNIT, "gbs_each_way_per_gpu": probe["gbs_each_way"],
                                 "what": "the same bytes up and down at once between page-locked memory and the device, no kernel, all ranks together"},
                "frac_of_copy_ceiling": (env.world * Ce * L * e_steps / dt / 1e9) / ceiling}
+        # the same call on ordinary (pageable) numpy memory, 8 channels: the slab goes through the context's page-locked
+        # staging ring (helper threads) instead of being copied by DMA directly
+        try:
+            Cp = min(8, Ce)
+            vnp = VelvetNoise(sample_rate_hz=FS, duration_seconds=0.03, num_impulses=30, num_outs=Cp, filtered_channels=tuple(range(Cp)), mode="LR",
+                              normalizer=None, seed=1)
+            px = np.ascontiguousarray(hx.array[:, :Cp])
+            vnp.convolve(px)
+            dtp = env.timed_wall(lambda: holder.__setitem__(slice(None), [vnp.convolve(px)]), 2)
+            e2e["pageable_input"] = {"value": env.world * Cp * L * 2 / dtp / 1e9, "unit": UNIT, "channels": Cp,
+                                     "note": "ordinary numpy input (staged through page-locked memory by a helper thread), pooled page-locked result"}
+            del px
+        except Exception as exc:
+            e2e["pageable_input"] = {"error": repr(exc)}
         del hx, holder
         R.trim_pinned_pool(0)
     except Exception as exc:  # report, do not hide

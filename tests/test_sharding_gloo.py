@@ -174,3 +174,33 @@ def test_optimize_velvet_noise_batch_world2_gloo(tmp_path):
     for r in range(world):
         assert np.array_equal(np.load(os.path.join(str(tmp_path), f"kappa_{r}.npy")), want)          # every rank: all clips, same bits
         assert np.array_equal(np.load(os.path.join(str(tmp_path), f"scores_{r}.npy")), info["scores"])  # and the full score matrix
+
+
+class _OracleBankAsync(_OracleBank):
+    """The same oracle-backed bank with the submit / collect interface of the CUDA bank, so that the refinement takes its
+    two-batches-in-flight path on CPU."""
+
+    def submit(self, requests, clip_ids):
+        out = []
+        for c, ks in zip(clip_ids, requests):
+            self.evaluations += len(ks)
+            if len(ks):
+                out.append(np.asarray(O.vn_grid_scores(self.clips[c], list(ks), sample_rate_hz=_FS, duration_seconds=_DUR, num_impulses=_NIMP, seed=1),
+                                      dtype=np.float32))
+        return np.concatenate(out) if out else np.zeros(0, np.float32)
+
+    def collect(self, handle):
+        return handle
+
+
+def test_refinement_with_two_batches_in_flight_equals_the_single_batch():
+    """The refinement splits the rank's clips into two half-batches that are evaluated alternately (the host work of one
+    runs under the kernels of the other on a GPU); a minimiser only sees its own values, so the result must not change."""
+    from vndecorrelate_b200 import optimization as OPT
+
+    clips = _batch_clips()
+    kw = dict(input_signals=clips, sample_rate_hz=_FS, duration_seconds=_DUR, num_impulses=_NIMP, seed=1, grid_size=_GRID, details=True)
+    one, info1 = OPT.optimize_velvet_noise_batch(_bank_factory=_OracleBank, **kw)
+    two, info2 = OPT.optimize_velvet_noise_batch(_bank_factory=_OracleBankAsync, **kw)
+    assert np.array_equal(one, two) and np.array_equal(info1["scores"], info2["scores"])
+    assert info1["evaluations_local"] == info2["evaluations_local"]

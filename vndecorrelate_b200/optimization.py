@@ -763,18 +763,22 @@ class _ClipBank:
             self._work = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
         return self._work, nbytes.value
 
-    def partials(self, requests: Sequence[Sequence[float]]):
-        """``requests[i]`` = strengths to evaluate on clip ``i``; returns the float64 partial sums
-        ``(total, OBJ_SLOTS)`` in request order (a CUDA tensor) and the per-clip counts."""
+    def partials(self, requests: Sequence[Sequence[float]], clip_ids: Sequence[int] | None = None):
+        """``requests[i]`` = strengths to evaluate on clip ``clip_ids[i]`` (default: clip ``i``); returns the float64
+        partial sums ``(total, OBJ_SLOTS)`` in request order (a CUDA tensor) and the per-request counts.  Everything is
+        enqueued on torch's current stream; nothing here waits for the device."""
         import torch
 
+        if clip_ids is None:
+            clip_ids = range(len(requests))
         counts = [len(r) for r in requests]
         total = sum(counts)
         out = torch.empty((total, N.OBJ_SLOTS), dtype=torch.float64, device=self.device)
         if total == 0:
             return out, counts
         flat = [float(k) for r in requests for k in r]
-        shared = len(set(counts)) == 1 and all(list(r) == list(requests[0]) for r in requests[1:])
+        shared = (len(requests) == self.n and len(set(counts)) == 1 and list(clip_ids) == list(range(self.n))
+                  and all(list(r) == list(requests[0]) for r in requests[1:]))
         lib = N.lib()
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -792,7 +796,7 @@ class _ClipBank:
                 ps = R.device_program(prog, self.device)
                 work, wbytes = self._workspace(max(counts))
                 base = 0
-                for i, n_i in enumerate(counts):
+                for i, n_i in zip(clip_ids, counts):
                     if n_i == 0:
                         continue
                     sub = N.TapProgramStruct(ps.words, ps.offsets + 4 * base, ps.n_words, n_i, ps.order, ps.apply_gain, ps.halo, ps.max_channel_words)
@@ -812,6 +816,25 @@ class _ClipBank:
             out.append(flat[base: base + n_i])
             base += n_i
         return out
+
+    def submit(self, requests: Sequence[Sequence[float]], clip_ids: Sequence[int]):
+        """Enqueue the evaluation of ``requests`` on the clips ``clip_ids`` and the download of its partial sums into
+        page-locked memory; returns a handle for ``collect``.  The host is free until then: the refinement keeps two such
+        batches in flight, so that scoring and the Brent step of one run under the kernels of the other."""
+        import torch
+
+        p, _ = self.partials(requests, clip_ids)
+        host = torch.empty(p.shape, dtype=p.dtype, pin_memory=True)
+        host.copy_(p, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(self.device))
+        return host, done, p  # p is kept alive until the copy has run
+
+    def collect(self, handle) -> np.ndarray:
+        """Scores (flat float32 array, request order) of a submitted batch."""
+        host, done, _ = handle
+        done.synchronize()
+        return vn_scores_from_partials(host.numpy(), **self.kw) if host.shape[0] else np.zeros(0, dtype=np.float32)
 
 
 def optimize_velvet_noise_batch(*, input_signals=None, sample_rate_hz: int, duration_seconds: float, num_impulses: int, seed: int = 1,
@@ -892,13 +915,50 @@ def optimize_velvet_noise_batch(*, input_signals=None, sample_rate_hz: int, dura
                 owner.append(ci - lo)
         owner = np.asarray(owner, dtype=np.int64)
 
-        def batch(xs, ids):  # ids ascend and the minimisers are listed clip by clip: a clip's requests are one contiguous run
+        def requests_of(xs, ids, clips_of_lane):  # ids ascend and the minimisers are listed clip by clip: a clip's requests are one contiguous run
             own = owner[ids]
-            cuts = np.searchsorted(own, np.arange(hi - lo + 1))
-            vals = bank.scores([xs[cuts[c]: cuts[c + 1]] for c in range(hi - lo)])
-            return np.concatenate(vals) if len(vals) else np.zeros(0, dtype=np.float32)
+            cuts = np.searchsorted(own, np.asarray(list(clips_of_lane) + [clips_of_lane[-1] + 1]))
+            return [xs[cuts[j]: cuts[j + 1]] for j in range(len(clips_of_lane))]
 
-        xs, funs, _ = lockstep_minimize_arrays(lows, highs, batch, xatol=1e-4)
+        n_local = hi - lo
+        if hasattr(bank, "submit") and n_local >= 2:
+            # Two half-batches of clips in flight: while the kernels of one half run, the host scores the other half,
+            # advances its minimisers and packs their next programs.  A minimiser only ever sees its own values, so
+            # the results do not depend on the split.
+            halves = [list(range(0, n_local // 2)), list(range(n_local // 2, n_local))]
+            lows, highs = np.asarray(lows, dtype=np.float64), np.asarray(highs, dtype=np.float64)
+            members = [np.nonzero(np.isin(owner, h))[0] for h in halves]
+            engines = [_BrentBatch(lows[m], highs[m], 1e-4) for m in members]
+            handles: list[Any] = [None, None]
+
+            def launch(h):
+                idx, xs_h = engines[h].pending()
+                if len(idx) == 0:
+                    handles[h] = None
+                    return
+                handles[h] = (idx, bank.submit(requests_of(xs_h, members[h][idx], halves[h]), halves[h]))
+
+            for h in (0, 1):
+                launch(h)
+            while handles[0] is not None or handles[1] is not None:
+                for h in (0, 1):
+                    if handles[h] is None:
+                        continue
+                    idx, handle = handles[h]
+                    engines[h].feed(idx, bank.collect(handle))
+                    launch(h)
+            xs = np.empty(len(owner), dtype=np.float64)
+            funs = np.empty(len(owner), dtype=np.float32)
+            for h in (0, 1):
+                x_h, f_h, _ = engines[h].results()
+                xs[members[h]] = x_h
+                funs[members[h]] = f_h
+        else:
+            def batch(xs, ids):
+                vals = bank.scores(requests_of(xs, ids, list(range(n_local))))
+                return np.concatenate(vals) if len(vals) else np.zeros(0, dtype=np.float32)
+
+            xs, funs, _ = lockstep_minimize_arrays(lows, highs, batch, xatol=1e-4)
         best_score = [np.inf] * (hi - lo)
         for x, fun, c in zip(xs, funs, owner):  # first strictly best minimum of each clip (optimization.py:150-153)
             if fun < best_score[c]:
