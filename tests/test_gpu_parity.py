@@ -651,6 +651,39 @@ def test_cfg5_full_shape_one_clip(api):
                    "evaluations": info["evaluations_local"], "evaluations_reference": ref["evaluations"]}, fh)
 
 
+@pytest.mark.parametrize("variant", ["1", "2"])
+def test_objective_tensor_memory_variants(api, monkeypatch, variant):
+    """The opt-in tensor-memory objective kernels (VND_OBJ_TMEM=1: 16 frames per lane x 20 warps, 2: 32 x 12) against the
+    default shared-memory kernel and the oracle: same argmin, scores within the float32 evaluation noise, the exact
+    max|theta| tracker identical (slots 6-9 of the partial sums), on whole tiles, a ragged last tile and a clip shorter
+    than the filter."""
+    from vndecorrelate_b200 import optimization as OPT
+    from vndecorrelate_b200 import taps as T
+
+    kw = dict(angle_limit=np.pi / 4, lambda_mean=5.0, lambda_skew=2.0, lambda_correlation=15.0, lambda_penalty=1e3)
+    for frames, grid in ((50000, 24), (3072 * 3, 7), (1000, 5)):
+        clips = np.stack([O.coloured_clip(i, frames).T for i in range(2)])
+        ks = np.linspace(0.0, 1.0, grid)
+        prog = T.kappa_family_program(ks, sample_rate_hz=48000, duration_seconds=0.03, num_impulses=30, envelope=(0.85, 0.55, 0.35, 0.2), seed=1,
+                                      frames=frames)
+        if prog is None:
+            prog = T.candidate_program([T.generate_tap_table(sample_rate_hz=48000, duration_seconds=0.03, num_impulses=30, num_outs=2, num_segments=4,
+                                                             log_distribution_strength=float(k), filtered_channels=(0,), seed=1) for k in ks],
+                                       (0.85, 0.55, 0.35, 0.2), frames)
+        monkeypatch.delenv("VND_OBJ_TMEM", raising=False)
+        base = OPT.vn_objective_partials(clips, prog)
+        monkeypatch.setenv("VND_OBJ_TMEM", variant)
+        got = OPT.vn_objective_partials(clips, prog)
+        monkeypatch.delenv("VND_OBJ_TMEM")
+        assert np.array_equal(got[..., 6:11], base[..., 6:11])  # tracked frames and frame counts: exact
+        assert np.allclose(got[..., :6], base[..., :6], rtol=2e-6, atol=1e-9)
+        s_got, s_base = OPT.vn_scores_from_partials(got, **kw), OPT.vn_scores_from_partials(base, **kw)
+        assert np.max(np.abs(s_got.astype(np.float64) - s_base.astype(np.float64))) <= 2e-4
+        ref = np.stack([O.vn_grid_scores(np.ascontiguousarray(c.T), ks, sample_rate_hz=48000, duration_seconds=0.03, num_impulses=30, seed=1) for c in clips])
+        assert np.max(np.abs(s_got.astype(np.float64) - ref.astype(np.float64))) <= 5e-4
+        assert [int(np.argmin(r)) for r in s_got] == [int(np.argmin(r)) for r in ref]
+
+
 def test_batch_optimiser_equals_clip_by_clip(api):
     """optimize_velvet_noise_batch on several clips returns, per clip, exactly what optimize_velvet_noise returns."""
     from vndecorrelate_b200 import optimization as OPT

@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(256) haas_objective_kernel(const TIn* __restri
 // per SM instead of 20 to hide the moments' dependent chains (issue 44 % instead of 63 %).
 static bool obj_tmem_disabled() {
   const char* e = getenv("VND_OBJ_TMEM");
-  return !(e && e[0] == '1');
+  return !(e && (e[0] == '1' || e[0] == '2'));
 }
 #define g_obj_disable_tmem obj_tmem_disabled()
 

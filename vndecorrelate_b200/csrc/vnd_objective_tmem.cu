@@ -37,15 +37,22 @@ namespace {
 using namespace tm;
 
 constexpr int OT_ROWS = 32;                 // rows of a tile = lanes of a TMEM quarter
-constexpr int OT_R = 96;                    // frames per row
-constexpr int OT_G = 3, OT_RG = 32;         // three groups of 32 consecutive frames per row and lane
-constexpr int OT_TILE = OT_ROWS * OT_R;     // 3072 frames
-constexpr int OT_PITCH = OT_R + 4;          // words between rows in shared memory (an odd number of 16-byte chunks)
-#ifndef VND_OT_WARPS
-#define VND_OT_WARPS 12
-#endif
-constexpr int OT_WARPS = VND_OT_WARPS;
-constexpr int OT_NT = OT_WARPS * 32;
+constexpr int OT_G = 3;                     // groups of RG consecutive frames per row and lane
+
+// Shape of the kernel: RG frames per lane and group (a row is 3 RG frames, the tile 32 rows), W warps per CTA.
+//   <32, 12>  one tcgen05.ld.x32 per tap and group; 163 registers -> 12 warps: 81 k evaluations/s (round 2, first build)
+//   <16, 20>  one tcgen05.ld.x16 per tap and group; fits the 96 registers of a 20-warp CTA, the warp count the
+//             shared-memory kernel needs to hide the polar moments' latencies
+template <int RG_, int W_>
+struct OtShape {
+  static constexpr int RG = RG_, W = W_;
+  static constexpr int R = OT_G * RG_;        // frames per row
+  static constexpr int TILE = OT_ROWS * R;
+  static constexpr int PITCH = R + 4;         // words between rows in shared memory (an odd number of 16-byte chunks)
+  static constexpr int NT = W_ * 32;
+  static_assert(((PITCH / 4) & 1) == 1 && R % 4 == 0, "conflict-free 16-byte row accesses");
+  __host__ __device__ static constexpr int near_max(int g) { return kCols - RG_ * (g + 1); }
+};
 
 // Per-warp scratch (words): the candidate's program | decoded operations per group (+ the slack words tap_list
 // prefetches) | segment tables per group (int4, 16-byte aligned).  Sized from the longest program of the family.
@@ -53,8 +60,6 @@ __host__ __device__ constexpr int ot_progwords(int mpw) { return (mpw + 3) & ~3;
 __host__ __device__ constexpr int ot_opstride(int mpw) { return (mpw + 4 + 3) & ~3; }
 __host__ __device__ constexpr int ot_maxseg(int mpw) { return mpw > 4 ? (mpw - 1) / 3 : 1; }
 __host__ __device__ constexpr int ot_warp_words(int mpw) { return ot_progwords(mpw) + OT_G * ot_opstride(mpw) + OT_G * ot_maxseg(mpw) * 4; }
-
-__host__ __device__ constexpr int ot_near_max(int g) { return kCols - OT_RG * (g + 1); }
 
 struct OtParams {
   ObjParams o;
@@ -67,6 +72,7 @@ extern __shared__ __align__(128) unsigned char ot_smem[];
 
 // Decode candidate `prog` (SEGMENTED block: S, (n_neg, n_pos, gain) x S, taps) for the warp: operation words per group
 // and, per group and segment, the tap counts with the number of LEADING tensor-memory taps of both lists.
+template <class T>
 __device__ __forceinline__ void decode_candidate(const int* __restrict__ prog, int nprog, int apply_gain, int* ops, int opstride, int4* segtab,
                                                  int smax, int lane) {
   const int S = prog[0];
@@ -78,14 +84,14 @@ __device__ __forceinline__ void decode_candidate(const int* __restrict__ prog, i
     for (int g = 0; g < OT_G; ++g) {
       int op = 0;
       if (k < ntaps) {
-        if (i <= ot_near_max(g)) {
+        if (i <= T::near_max(g)) {
           op = i;
         } else {
-          const int o = i + OT_RG * g, A = o & 3, oal = o - A;
-          const int blk = oal / OT_R, w = oal - blk * OT_R;
-          int kx = (OT_R - w) >> 2;
+          const int o = i + T::RG * g, A = o & 3, oal = o - A;
+          const int blk = oal / T::R, w = oal - blk * T::R;
+          int kx = (T::R - w) >> 2;
           if (kx > 31) kx = 31;
-          op = kOpFar | (A << 24) | (kx << 16) | (blk * OT_PITCH + w);
+          op = kOpFar | (A << 24) | (kx << 16) | (blk * T::PITCH + w);
         }
       }
       ops[g * opstride + k] = op;
@@ -95,7 +101,7 @@ __device__ __forceinline__ void decode_candidate(const int* __restrict__ prog, i
     const int g = idx / S, s = idx - g * S;
     const int* tq = taps;
     for (int k = 0; k < s; ++k) tq += prog[1 + 3 * k] + prog[2 + 3 * k];
-    const int n_neg = prog[1 + 3 * s], n_pos = prog[2 + 3 * s], nmax = ot_near_max(g);
+    const int n_neg = prog[1 + 3 * s], n_pos = prog[2 + 3 * s], nmax = T::near_max(g);
     int a = 0, b = 0;
     while (a < n_neg && tq[a] <= nmax) ++a;
     while (b < n_pos && tq[n_neg + b] <= nmax) ++b;
@@ -103,7 +109,9 @@ __device__ __forceinline__ void decode_candidate(const int* __restrict__ prog, i
   }
 }
 
-__global__ void __launch_bounds__(OT_NT, 1) vn_objective_tmem_kernel(const OtParams P) {
+template <class T>
+__global__ void __launch_bounds__(T::NT, 1) vn_objective_tmem_kernel(const OtParams P) {
+  constexpr int OT_RG = T::RG, OT_R = T::R, OT_TILE = T::TILE, OT_PITCH = T::PITCH, OT_NT = T::NT, OT_WARPS = T::W;
   const ObjParams& p = P.o;
   uint32_t* tm_slot = reinterpret_cast<uint32_t*>(ot_smem);
   float* s_in = reinterpret_cast<float*>(ot_smem + 16);
@@ -177,14 +185,16 @@ __global__ void __launch_bounds__(OT_NT, 1) vn_objective_tmem_kernel(const OtPar
     }
     __syncthreads();
     tmem_fence_after();
-    // the tile into tensor memory, once per quarter: the warps of a quarter share its sixteen 32-column units
+    // the tile into tensor memory, once per quarter: the warps of a quarter share its sixteen 32-column units; row m
+    // holds x[t0 + R m + c], i.e. 16-byte chunk c / 4 of the staged rows m, m + 1, ... (R / 4 chunks per staged row)
     for (int u = warp >> 2; u < kUnits; u += (OT_WARPS + 3 - q) / 4) {
-      const int col0 = 32 * u, blk = col0 / OT_R, w = col0 - blk * OT_R;  // a unit never straddles a block (96 = 3 x 32)
-      const float4* src = reinterpret_cast<const float4*>(s_in + (lane + blk) * OT_PITCH + w);
       float4 v[8];
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) v[jj] = src[jj];
-      tmem_st32(tbase + (uint32_t)col0, v);
+      for (int jj = 0; jj < 8; ++jj) {
+        const int c4 = 8 * u + jj, blk = c4 / (OT_R / 4), w4 = c4 - blk * (OT_R / 4);
+        v[jj] = *reinterpret_cast<const float4*>(s_in + (lane + blk) * OT_PITCH + 4 * w4);
+      }
+      tmem_st32(tbase + (uint32_t)(32 * u), v);
     }
     tmem_wait_st();
     tmem_fence_before();
@@ -198,7 +208,7 @@ __global__ void __launch_bounds__(OT_NT, 1) vn_objective_tmem_kernel(const OtPar
       __syncwarp();
       for (int i = lane; i < nprog; i += 32) myprog[i] = p.words[w0 + i];
       __syncwarp();
-      decode_candidate(myprog, nprog, p.apply_gain, myops, opstride, mysegs, smax, lane);
+      decode_candidate<T>(myprog, nprog, p.apply_gain, myops, opstride, mysegs, smax, lane);
       __syncwarp();
       const int S = myprog[0];
       LaneAcc2 b{{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, 0.f, 1.f, 0.f, 1.f, -1.f, -1.f};
@@ -207,7 +217,7 @@ __global__ void __launch_bounds__(OT_NT, 1) vn_objective_tmem_kernel(const OtPar
       for (int g = 0; g < OT_G; ++g) {
         float yv[OT_RG];
 #pragma unroll
-        for (int r = 0; r < OT_RG; ++r) yv[r] = 0.0f;
+        for (int r = 0; r < OT_RG; ++r) yv[r] = 0.0f;  // (run_segments assigns; keeps the compiler quiet)
         const int* ops = myops + g * opstride;
         run_segments<false, false>(mysegs + g * smax, 0, S, ops, tbase + (uint32_t)(OT_RG * g), row, yv);
         const float4* r1 = reinterpret_cast<const float4*>(s_x1 + lane * OT_PITCH + OT_RG * g);
@@ -276,14 +286,26 @@ long long ot_max_chunks(long long tiles, int n_clips, int sm_count) {
 
 }  // namespace
 
+using OtWide = OtShape<32, 12>;
+using OtNarrow = OtShape<16, 20>;
+
+// VND_OBJ_TMEM: 1 = 16 frames per lane x 20 warps, 2 = 32 frames per lane x 12 warps (anything else: the caller's
+// shared-memory kernel)
+static int ot_variant() {
+  const char* e = getenv("VND_OBJ_TMEM");
+  return e ? atoi(e) : 0;
+}
+
 size_t objective_tmem_workspace_bytes(long long frames, int n_clips, int n_cand, int sm_count) {
-  const long long tiles = ceil_div<long long>(frames, OT_TILE);
+  const long long tiles = ceil_div<long long>(frames, OtNarrow::TILE);  // the finer tiling of the two shapes
   return (size_t)n_clips * ot_max_chunks(tiles, n_clips, sm_count) * n_cand * OBJ_SLOTS * 8 + 256;
 }
 
 // VND_EUNSUPPORTED (no error text) when the program family does not qualify; the caller then runs vn_objective_kernel.
-int vn_objective_tmem_launch(const float* clips, long long frames, int n_clips, long long clip_stride, long long chan_stride,
-                             const vnd_tap_program* cand, double* partials, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+template <class T>
+static int ot_launch(const float* clips, long long frames, int n_clips, long long clip_stride, long long chan_stride,
+                     const vnd_tap_program* cand, double* partials, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  constexpr int OT_R = T::R, OT_TILE = T::TILE, OT_PITCH = T::PITCH, OT_NT = T::NT, OT_WARPS = T::W;
   const int mpw = cand->max_channel_words > 0 ? cand->max_channel_words : 1;
   int halo = cand->halo > 0 ? cand->halo : 0;
   if (halo > frames) halo = (int)frames;
@@ -342,12 +364,21 @@ int vn_objective_tmem_launch(const float* clips, long long frames, int n_clips, 
   P.nblk = nblk;
   P.mpw = mpw;
   const size_t smem = fixed + (size_t)cpg * OBJ_SLOTS * 8;
-  VND_CUDA_OK(cudaFuncSetAttribute(vn_objective_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VND_CUDA_OK(cudaFuncSetAttribute(vn_objective_tmem_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)n_chunks, (unsigned)n_clips, (unsigned)groups);
-  vn_objective_tmem_kernel<<<grid, OT_NT, smem, st>>>(P);
+  vn_objective_tmem_kernel<T><<<grid, OT_NT, smem, st>>>(P);
   rc = after_launch("vn_objective_tmem_kernel");
   if (rc) return rc;
   return obj_combine_launch(P.o.chunk_partials, partials, n_clips, (int)n_chunks, cand->channels, st);
+}
+
+int vn_objective_tmem_launch(const float* clips, long long frames, int n_clips, long long clip_stride, long long chan_stride,
+                             const vnd_tap_program* cand, double* partials, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  switch (ot_variant()) {
+    case 1: return ot_launch<OtNarrow>(clips, frames, n_clips, clip_stride, chan_stride, cand, partials, workspace, workspace_bytes, st);
+    case 2: return ot_launch<OtWide>(clips, frames, n_clips, clip_stride, chan_stride, cand, partials, workspace, workspace_bytes, st);
+    default: return VND_EUNSUPPORTED;
+  }
 }
 
 }  // namespace vnd

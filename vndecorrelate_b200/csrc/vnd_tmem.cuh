@@ -67,7 +67,10 @@ __device__ __forceinline__ void tmem_ld(float (&v)[RG], uint32_t taddr) {
 // compiler from moving their consumers above it.
 template <int RG>
 __device__ __forceinline__ void tmem_wait_ld(float (&v)[RG]) {
-  if constexpr (RG == 32) {
+  static_assert(RG == 16 || RG == 32 || RG == 48 || RG == 64, "outputs per thread");
+  if constexpr (RG == 16) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : VND_IO16(v, 0)::"memory");
+  } else if constexpr (RG == 32) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" : VND_IO16(v, 0), VND_IO16(v, 16)::"memory");
   } else if constexpr (RG == 48) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" : VND_IO16(v, 0), VND_IO16(v, 16), VND_IO16(v, 32)::"memory");
@@ -144,7 +147,9 @@ VND_PACKED_OP(mul2, "mul")
 // packed adds (or subtracts).
 template <int RG>
 __device__ __forceinline__ void near_issue(float (&t)[RG], uint32_t tcol) {
-  if constexpr (RG == 32) {
+  if constexpr (RG == 16) {
+    tmem_ld<16, 0>(t, tcol);
+  } else if constexpr (RG == 32) {
     tmem_ld<32, 0>(t, tcol);
   } else if constexpr (RG == 48) {
     tmem_ld<32, 0>(t, tcol);
