@@ -144,7 +144,9 @@ int vnd_haas_dev(const vnd_signal* x, const vnd_signal* out, int32_t delay, int3
 
 /* In-place stereo helpers on a (frames, 2) signal, F32 or F64 (utils/dsp.py:21-63, :124-167).
  * op: 0 LR_to_MS, 1 MS_to_LR, 2 apply_stereo_width(width), 3 encode_signal_to_side_channel(x, y)
- * (x = `dry`, y = `a`), 4 rms_normalize(dry, a) DUAL_MONO (needs workspace of 2*channels floats). */
+ * (x = `dry`, y = `a`), 4 rms_normalize(dry, a) DUAL_MONO.  Op 4 sums each signal in the order numpy uses for its
+ * layout: frame by frame for a C-order (frames, 2) signal, pairwise per column for a planar / Fortran-ordered one; workspace:
+ * 64 bytes, plus 8 * (frames / 64 + 8) when a signal is planar. */
 int vnd_stereo_op_dev(const vnd_signal* a, const vnd_signal* dry, int32_t op, double width,
                       void* workspace, size_t workspace_bytes, void* stream);
 

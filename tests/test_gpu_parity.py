@@ -203,6 +203,44 @@ def test_polar_coordinates(api, c):
     assert len(two) == 2 and G.sha(two[0]) == c["sha256"]["radii"]
 
 
+@pytest.mark.parametrize("frames", [100, 4099, 250_774])
+def test_rms_order_follows_the_layout_like_numpy(api, frames):
+    """numpy sums np.mean(np.square(a), axis=0) along the axis of the smallest stride: frame by frame (a sequential running
+    sum) for a C-order (frames, 2) array, pairwise per column for a Fortran-ordered / planar one - 6e-5 apart in float32 on a
+    250 k-frame file.  decorrelate() and rms_normalize() must follow the layout of each array the way the reference does."""
+    from vndecorrelate_b200.utils import dsp
+
+    rng = np.random.default_rng(frames)
+    xc = (rng.standard_normal((frames, 2)) * 0.3).astype(np.float32)
+    xf = np.asfortranarray(xc)                  # same values, planar in memory (what `planar_array.T` gives a user)
+    taps = O.class_taps(sample_rate_hz=44100, seed=1)
+    vn = api.VelvetNoise(sample_rate_hz=44100, duration_seconds=0.03, num_impulses=30, seed=1)
+    want_c, want_f = O.vn_decorrelate(xc, taps), O.vn_decorrelate(xf, taps)
+    assert G.same_bits(vn.decorrelate(xc), want_c)
+    assert G.same_bits(vn.decorrelate(xf), want_f)
+    if frames > 100000:
+        assert not np.array_equal(want_c, want_f)  # the two orders really differ at this length
+    import torch
+
+    got_t = vn.decorrelate(torch.from_numpy(np.ascontiguousarray(xc.T)).cuda().t())  # planar CUDA tensor, (frames, 2) view
+    assert G.same_bits(got_t.cpu().numpy(), want_f)
+    # the helper itself, every combination of layouts, float32 and float64
+    for dt in (np.float32, np.float64):
+        y0 = (rng.standard_normal((frames, 2)) * 0.1).astype(dt)
+        for x in (xc.astype(dt), np.asfortranarray(xc.astype(dt))):
+            for y in (y0.copy(), np.asfortranarray(y0)):
+                want = y.copy(order="K")
+                O.rms_match(x, want)
+                got = y.copy(order="K")
+                dsp.rms_normalize(x, got)
+                assert G.same_bits(np.ascontiguousarray(got), np.ascontiguousarray(want)), (dt, x.flags.f_contiguous, y.flags.f_contiguous)
+                want = y.copy(order="K")  # STEREO mode: axis=None statistics run over the array in memory order
+                O.rms_match(x, want, stereo_mode=True)
+                got = y.copy(order="K")
+                dsp.rms_normalize(x, got, mode=dsp.NormalizeMode.STEREO)
+                assert G.same_bits(np.ascontiguousarray(got), np.ascontiguousarray(want)), ("stereo", dt, x.flags.f_contiguous, y.flags.f_contiguous)
+
+
 def test_rms_normalize_reference_known_answers(api):
     """The reference's own test of rms_normalize (tests/test_dsp.py:119-142), float64: 1-D, DUAL_MONO, STEREO (known value
     0.55893258) and a 1-D input against a 2-D output in STEREO mode."""

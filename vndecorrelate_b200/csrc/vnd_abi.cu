@@ -21,6 +21,8 @@ int sparse_fir_launch(const vnd_signal* x, const vnd_signal* y, const vnd_tap_pr
 int vn_stereo_launch(const vnd_signal* x, void* out, int out_dtype, long long o_st, long long o_sc, const vnd_tap_program* taps,
                      int prog_words, const vnd_epilogue* ep, const float* gains, int delay, int delay_ch, cudaStream_t st);
 int seq_sumsq_launch(const vnd_signal* a, const vnd_signal* b, void* sums, cudaStream_t st);
+int colsumsq_launch(const vnd_signal* a, const vnd_signal* b, void* sums, void* leaf, size_t leaf_bytes, cudaStream_t st);
+size_t colsumsq_workspace_bytes(long long frames);
 int rms_gain_launch(const void* sums, void* gains, int channels, long long frames, int dtype, cudaStream_t st);
 int place_launch(const float* y, long long y_st, long long y_sc, long long frames, int channels, const vnd_signal* out,
                  const float* gains, int delay, int delay_ch, cudaStream_t st);
@@ -137,7 +139,9 @@ extern "C" int vnd_sparse_fir_dev(const vnd_signal* x, const vnd_signal* y, cons
 extern "C" int vnd_vn_decorrelate_workspace(int64_t frames, int32_t channels, const vnd_epilogue* ep, size_t* bytes) {
   VND_REQUIRE(bytes != nullptr && ep != nullptr, VND_EINVAL, "null argument");
   VND_REQUIRE(frames >= 0 && channels >= 0, VND_EINVAL, "negative extent");
-  *bytes = 256 + align_up((size_t)channels * 3 * sizeof(float), 256) + (size_t)frames * channels * sizeof(float);
+  // status words | sums and gains | leaf sums of the pairwise order (planar inputs) | float32 scratch of the result
+  *bytes = 256 + align_up((size_t)channels * 3 * sizeof(float), 256) + align_up(colsumsq_workspace_bytes(frames), 256) +
+           (size_t)frames * channels * sizeof(float);
   return VND_OK;
 }
 
@@ -166,7 +170,9 @@ extern "C" int vnd_vn_decorrelate_dev(const vnd_signal* x, const vnd_signal* out
   char* ws = reinterpret_cast<char*>(workspace);
   float* sums = reinterpret_cast<float*>(ws);
   float* gains = sums + 2 * (size_t)C;
-  float* scratch = reinterpret_cast<float*>(ws + align_up((size_t)C * 3 * sizeof(float), 256));
+  char* leaf = ws + align_up((size_t)C * 3 * sizeof(float), 256);
+  const size_t leaf_bytes = align_up(colsumsq_workspace_bytes(L), 256);
+  float* scratch = reinterpret_cast<float*>(leaf + leaf_bytes);
 
   if (L == 0 || C == 0) return place_launch(nullptr, 0, 0, 0, C, out, nullptr, delay, dch, st);
 
@@ -192,7 +198,7 @@ extern "C" int vnd_vn_decorrelate_dev(const vnd_signal* x, const vnd_signal* out
   if (ep->rms_normalize) {
     vnd_signal xa = *x;
     xa.channels = C;
-    if ((rc = seq_sumsq_launch(&xa, &y, sums, st))) return rc;
+    if ((rc = colsumsq_launch(&xa, &y, sums, leaf, leaf_bytes, st))) return rc;  // x in the order its layout gives it in numpy
     if ((rc = rms_gain_launch(sums, gains, C, L, VND_F32, st))) return rc;
     g = gains;
   }
@@ -232,10 +238,11 @@ extern "C" int vnd_stereo_op_dev(const vnd_signal* a, const vnd_signal* dry, int
   }
   if (op == 4) {
     const size_t esz = a->dtype == VND_F64 ? 8 : 4;
-    VND_REQUIRE(workspace != nullptr && workspace_bytes >= 6 * esz, VND_ENOMEM, "rms workspace needs %zu bytes", 6 * esz);
+    VND_REQUIRE(workspace != nullptr && workspace_bytes >= 64, VND_ENOMEM, "rms workspace needs at least 64 bytes");
     char* sums = reinterpret_cast<char*>(workspace);
     char* gains = sums + 4 * esz;
-    if ((rc = seq_sumsq_launch(dry, a, sums, st))) return rc;
+    // planar (Fortran-ordered) signals are summed in numpy's pairwise order and need 64 + 8 (frames / 64 + 8) bytes
+    if ((rc = colsumsq_launch(dry, a, sums, sums + 64, workspace_bytes - 64, st))) return rc;
     if ((rc = rms_gain_launch(sums, gains, 2, a->frames, a->dtype, st))) return rc;
     return stereo_op_launch(a, nullptr, 4, 0.0, gains, st);
   }
@@ -942,7 +949,8 @@ extern "C" int vnd_stereo_op_host(vnd_ctx* ctx, const vnd_signal* a, const vnd_s
   cudaStream_t st = ctx->streams[0];
   void *dA = nullptr, *dD = nullptr, *work = nullptr;
   if ((rc = arena(ctx, S_IN, da.elems * esize(a->dtype), &dA))) return rc;
-  if ((rc = arena(ctx, S_WORK, 256, &work))) return rc;
+  const size_t wbytes = 64 + colsumsq_workspace_bytes(a->frames);
+  if ((rc = arena(ctx, S_WORK, wbytes, &work))) return rc;
   if (da.elems) VND_CUDA_OK(cudaMemcpyAsync(dA, a->data, da.elems * esize(a->dtype), cudaMemcpyHostToDevice, st));
   vnd_signal ad = *a, dd{};
   ad.data = dA;
@@ -955,7 +963,7 @@ extern "C" int vnd_stereo_op_host(vnd_ctx* ctx, const vnd_signal* a, const vnd_s
     dd = *dry;
     dd.data = dD;
   }
-  if ((rc = vnd_stereo_op_dev(&ad, (op == 3 || op == 4) ? &dd : nullptr, op, width, work, 256, st))) return rc;
+  if ((rc = vnd_stereo_op_dev(&ad, (op == 3 || op == 4) ? &dd : nullptr, op, width, work, wbytes, st))) return rc;
   if (da.elems) VND_CUDA_OK(cudaMemcpyAsync(a->data, dA, da.elems * esize(a->dtype), cudaMemcpyDeviceToHost, st));
   VND_CUDA_OK(cudaStreamSynchronize(st));
   return VND_OK;

@@ -262,10 +262,15 @@ int pairwise_launch(const T* a, long long n, T* leafsum, T* out, cudaStream_t st
 
 }  // namespace
 
-// launchers of vnd_post.cu (numpy axis-0 order sums for 2-D DUAL_MONO)
-int seq_sumsq_launch(const vnd_signal* a, const vnd_signal* b, void* sums, cudaStream_t st);
-
 size_t dsp_workspace_bytes(long long elems) { return ((size_t)(elems / 64 + 4) + 64) * 8 * 2 + 1024; }
+
+// numpy-order PAIRWISE sum of squares of one contiguous column (what np.mean(np.square(a), axis=0) does for a column of a
+// Fortran-ordered / planar array: numpy puts the inner loop on the axis with the smallest stride).  `leaf` holds n / 64 + 4
+// elements of the column's type.
+int pairwise_sumsq_launch(const void* col, int dtype, long long n, void* leaf, void* out, cudaStream_t st) {
+  if (dtype == VND_F64) return pairwise_launch<double, true>((const double*)col, n, (double*)leaf, (double*)out, st);
+  return pairwise_launch<float, true>((const float*)col, n, (float*)leaf, (float*)out, st);
+}
 
 // rms_normalize in every shape / mode combination (utils/dsp.py:87-109).  x and y: contiguous C-order (frames, ch) or
 // 1-D, same dtype.  axis=None when the signal is 1-D or the mode is STEREO, axis=0 otherwise.

@@ -704,6 +704,45 @@ int seq_sumsq_launch(const vnd_signal* a, const vnd_signal* b, void* sums, cudaS
   return after_launch("seq_sumsq_kernel");
 }
 
+int pairwise_sumsq_launch(const void* col, int dtype, long long n, void* leaf, void* out, cudaStream_t st);
+
+// numpy reduces np.mean(np.square(a), axis=0) with its inner loop on the axis of the SMALLEST stride: a C-order (frames,
+// channels) array is summed frame by frame (a sequential running sum per column), a Fortran-ordered / planar one column by
+// column with the pairwise algorithm.  The two give different float32 sums (6e-5 relative on a 250 k-frame file), so the
+// order follows the layout of each signal, as it does in the reference.
+static bool sums_pairwise(const vnd_signal* s) {
+  if (s->channels <= 0 || s->frames <= 1) return false;
+  const long long st = s->stride_t < 0 ? -s->stride_t : s->stride_t, sc = s->stride_c < 0 ? -s->stride_c : s->stride_c;
+  return s->channels > 1 ? (st == 1 && sc >= s->frames) : false;
+}
+size_t colsumsq_workspace_bytes(long long frames) { return ((size_t)(frames / 64) + 8) * 8; }
+
+// sums[0 .. Ca) for a's columns, then b's; `leaf` (colsumsq_workspace_bytes) is only touched for planar signals
+int colsumsq_launch(const vnd_signal* a, const vnd_signal* b, void* sums, void* leaf, size_t leaf_bytes, cudaStream_t st) {
+  const bool pa = sums_pairwise(a), pb = b && sums_pairwise(b);
+  if (!pa && !pb) return seq_sumsq_launch(a, b, sums, st);
+  const size_t es = a->dtype == VND_F64 ? 8 : 4;
+  VND_REQUIRE(leaf != nullptr && leaf_bytes >= colsumsq_workspace_bytes(a->frames), VND_ENOMEM, "workspace too small for a planar signal's pairwise sums");
+  int rc;
+  const vnd_signal* sig[2] = {a, b};
+  const bool pw[2] = {pa, pb};
+  char* out = reinterpret_cast<char*>(sums);
+  for (int k = 0; k < 2; ++k) {
+    if (!sig[k]) continue;
+    if (!pw[k]) {
+      if ((rc = seq_sumsq_launch(sig[k], nullptr, out, st))) return rc;
+    } else {
+      for (int c = 0; c < sig[k]->channels; ++c) {
+        const char* col = reinterpret_cast<const char*>(sig[k]->data) + (long long)c * sig[k]->stride_c * (long long)es;
+        VND_REQUIRE(sig[k]->stride_t == 1 && sig[k]->stride_c > 0, VND_EUNSUPPORTED, "planar signals with negative strides are not supported");
+        if ((rc = pairwise_sumsq_launch(col, a->dtype, sig[k]->frames, leaf, out + (size_t)c * es, st))) return rc;
+      }
+    }
+    out += (size_t)sig[k]->channels * es;
+  }
+  return VND_OK;
+}
+
 int rms_gain_launch(const void* sums, void* gains, int channels, long long frames, int dtype, cudaStream_t st) {
   if (channels == 0) return VND_OK;
   const unsigned blocks = (unsigned)ceil_div(channels, 128);

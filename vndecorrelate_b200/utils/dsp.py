@@ -107,16 +107,20 @@ def _stereo_op(a, op: int, width: float = 0.0, dry=None) -> None:
         if dry is not None:
             dry = dry.to(a.dtype)
             sd = R.torch_signal(dry)
-        work = torch.empty(256, dtype=torch.uint8, device=a.device)
+        nbytes = 128 + 8 * (a.shape[0] // 64 + 8)  # op 4 on planar tensors keeps the leaf sums of numpy's pairwise order here
+        work = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
         N.check(N.lib().vnd_stereo_op_dev(C.byref(sa), C.byref(sd) if sd is not None else None, op, float(width),
-                                          work.data_ptr(), 256, R.torch_stream_ptr(a)), "vnd_stereo_op_dev")
+                                          work.data_ptr(), nbytes, R.torch_stream_ptr(a)), "vnd_stereo_op_dev")
         return
     _float_array(a, "signal")
-    work = a if (a.flags.c_contiguous and a.flags.writeable) else np.ascontiguousarray(a)
+    # C-order and planar (Fortran-ordered) arrays go to the device as they are: rms_normalize sums a signal in the order
+    # numpy uses for its layout (sequential along frames for C order, pairwise per column for planar)
+    work = a if (R.dense(a) is a and a.flags.writeable) else np.ascontiguousarray(a)
     sa = R.host_signal(work)
     sd = None
     if dry is not None:
-        dry = np.ascontiguousarray(dry, dtype=a.dtype)
+        dry = dry if dry.dtype == a.dtype else dry.astype(a.dtype)
+        dry = R.dense(dry)
         sd = R.host_signal(dry)
     ctx = R.HostContext.get()
     N.check(N.lib().vnd_stereo_op_host(ctx.handle, C.byref(sa), C.byref(sd) if sd is not None else None, op, float(width)), "vnd_stereo_op_host")
@@ -151,13 +155,18 @@ def encode_signal_to_side_channel(input_signal, decorrelated_signal) -> None:
     _stereo_op(decorrelated_signal, _OP_ENCODE, dry=input_signal)
 
 
-def _flat_inplace(fn_host, fn_dev, arrays, make_args):
+def _flat_inplace(fn_host, fn_dev, arrays, flat: bool):
     """Run an in-place device helper on contiguous views of ``arrays`` (numpy: upload / run / download inside the host
     call; CUDA tensors: on torch's stream), copying back when a contiguous temporary had to be made."""
     first = arrays[-1]
+    # numpy reduces with axis=None in MEMORY order: a Fortran-ordered (planar) 2-D array is one contiguous run of its
+    # transpose, so hand that view over (same memory, same in-place result) instead of a C-order copy
     if R.is_torch_tensor(first):
         import torch
 
+        if flat:
+            arrays = [a.t() if (a.dim() == 2 and not a.is_contiguous() and a.t().is_contiguous()) else a for a in arrays]
+        first = arrays[-1]
         work = [a if a.is_contiguous() else a.contiguous() for a in arrays]
         nbytes = C.c_size_t()
         N.check(N.lib().vnd_dsp_workspace(max(int(w.numel()) for w in work), C.byref(nbytes)), "vnd_dsp_workspace")
@@ -167,6 +176,8 @@ def _flat_inplace(fn_host, fn_dev, arrays, make_args):
         if work[-1] is not arrays[-1]:
             arrays[-1].copy_(work[-1])
         return
+    if flat:
+        arrays = [a.T if (a.ndim == 2 and a.flags.f_contiguous and not a.flags.c_contiguous) else a for a in arrays]
     work = [a if a.flags.c_contiguous else np.ascontiguousarray(a) for a in arrays]
     if not work[-1].flags.writeable:
         raise ValueError("output array is read-only")
@@ -214,7 +225,7 @@ def rms_normalize(input_signal, output_signal, mode: NormalizeMode = NormalizeMo
         N.check(lib.vnd_rms_normalize_dev(C.byref(_sig(w[0])), xn, C.byref(_sig(w[1])), yn, int(stereo), float(epsilon), ws, nbytes, stream),
                 "vnd_rms_normalize_dev")
 
-    _flat_inplace(host, dev, [input_signal, output_signal], None)
+    _flat_inplace(host, dev, [input_signal, output_signal], True)
 
 
 def peak_normalize(input_signal, mode: NormalizeMode = NormalizeMode.DUAL_MONO, epsilon: float = EPSILON) -> None:
@@ -234,7 +245,7 @@ def peak_normalize(input_signal, mode: NormalizeMode = NormalizeMode.DUAL_MONO, 
     def dev(w, ws, nbytes, stream):
         N.check(lib.vnd_peak_normalize_dev(C.byref(_sig(w[0])), nd, int(stereo), float(epsilon), ws, nbytes, stream), "vnd_peak_normalize_dev")
 
-    _flat_inplace(host, dev, [input_signal], None)
+    _flat_inplace(host, dev, [input_signal], nd == 1 or stereo)
 
 
 def polar_coordinates(left, right, mode: LayoutMode = "MS", semicircular: bool = True, normalize: bool = True, compute_weights: bool = True):
