@@ -311,11 +311,11 @@ def run_reference(args) -> None:
     workers = max(1, cores)
     ch, frames = 4, 960_000  # 20 s @ 48 kHz per worker and step
     sample = f"{workers} processes x {ch} channels x {frames} frames (20 s @ 48 kHz), C-order (frames, channels) fp32, per step"
-    warm = max(0, min(args.warmup, 1))  # one warm-up pass is enough for a CPU loop (and keeps the arm within minutes)
+    warm = max(0, min(args.warmup, 10))  # a step is a bounded sample (~0.3 s): K and W are honoured up to 100 / 10
     for _ in range(warm):
         cpu_fir_rate(workers, ch, frames)
     t_total = 0.0
-    steps = max(1, min(args.steps, 5))
+    steps = max(1, min(args.steps, 100))
     for _ in range(steps):
         _, dt = cpu_fir_rate(workers, ch, frames)
         t_total += dt
@@ -587,8 +587,14 @@ def run_cfg3(env: Env, args, lib, N, R, VelvetNoise, C):
             vnp = VelvetNoise(sample_rate_hz=FS, duration_seconds=0.03, num_impulses=30, num_outs=Cp, filtered_channels=tuple(range(Cp)), mode="LR",
                               normalizer=None, seed=1)
             px = np.ascontiguousarray(hx.array[:, :Cp])
-            vnp.convolve(px)
-            dtp = env.timed_wall(lambda: holder.__setitem__(slice(None), [vnp.convolve(px)]), 2)
+            holder.clear()
+            holder.append(vnp.convolve(px))
+
+            def pageable_step():
+                holder.clear()  # the result block goes back to the pool before the next call takes it
+                holder.append(vnp.convolve(px))
+
+            dtp = env.timed_wall(pageable_step, 2)
             e2e["pageable_input"] = {"value": env.world * Cp * L * 2 / dtp / 1e9, "unit": UNIT, "channels": Cp,
                                      "note": "ordinary numpy input (staged through page-locked memory by a helper thread), pooled page-locked result"}
             del px

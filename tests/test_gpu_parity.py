@@ -722,6 +722,28 @@ def test_objective_tensor_memory_variants(api, monkeypatch, variant):
         assert [int(np.argmin(r)) for r in s_got] == [int(np.argmin(r)) for r in ref]
 
 
+def test_empty_clip_is_an_error_not_a_crash(api):
+    """An empty signal has no max|theta|: the reference raises numpy's ValueError; the C ABI answers VND_EINVAL (it used to
+    divide by zero while planning the launch)."""
+    import ctypes as C_
+
+    from vndecorrelate_b200 import _native as N
+    from vndecorrelate_b200 import optimization as OPT
+    from vndecorrelate_b200 import runtime as R
+    from vndecorrelate_b200 import taps as T
+
+    cands = [api.VelvetNoise(sample_rate_hz=48000, log_distribution_strength=k, normalizer=None, filtered_channels=(0,), mode="LR", seed=1) for k in (0.0, 1.0)]
+    with pytest.raises(ValueError):
+        OPT.grid_scan(np.zeros((0, 2), dtype=np.float32), cands, angle_limit=np.pi / 4, lambda_mean=5.0, lambda_skew=2.0, lambda_correlation=15.0,
+                      lambda_penalty=1e3)
+    prog = T.candidate_program([c.velvet_noise for c in cands], cands[0].segment_envelope, 100)
+    out = np.zeros((1, 2, N.OBJ_SLOTS))
+    dummy = np.zeros(4, dtype=np.float32)
+    ps = prog.host_struct()
+    rc = N.lib().vnd_vn_objective_batch_host(R.HostContext.get().handle, dummy.ctypes.data, 0, 1, 0, 0, C_.byref(ps), out.ctypes.data)
+    assert rc == N.VND_EINVAL and b"empty" in N.lib().vnd_last_error()
+
+
 def test_batch_optimiser_equals_clip_by_clip(api):
     """optimize_velvet_noise_batch on several clips returns, per clip, exactly what optimize_velvet_noise returns."""
     from vndecorrelate_b200 import optimization as OPT

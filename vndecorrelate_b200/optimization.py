@@ -291,6 +291,8 @@ def symmetry_aware_objective(input_signal, decorrelator: Decorrelator, *, angle_
 def _scan(input_signal, decorrelators, kw) -> np.ndarray:
     if len(decorrelators) == 0:
         return np.array([])
+    if len(input_signal) == 0:  # the reference takes max(|theta|) of the frames (optimization.py:41-43): numpy's own error
+        raise ValueError("zero-size array to reduction operation maximum which has no identity")
     if all(_is_vn_candidate(d) for d in decorrelators):
         x = _as_stereo_f32(input_signal)
         prog = _vn_family_program(decorrelators, x.shape[0])
