@@ -619,3 +619,28 @@ def test_array_brent_equals_the_coroutine_abscissa_by_abscissa():
         assert fun.dtype == dtype
         for i in range(n):
             assert seq_a[i] == seq_b[i] and want[i].x == x[i] and want[i].fun == fun[i] and want[i].nfev == nfev[i], i
+
+
+def test_fir_kernels_have_no_contracted_multiply_add():
+    """Floating-point contract: the reference rounds after every numpy ufunc, so no FIR / post-processing
+    kernel may contain a multiply-add with a real addend.  ptxas was seen contracting a packed `mul.rn.f32x2` followed by
+    `add.rn.f32x2` into FFMA2 (one rounding instead of two) despite -fmad=false when both landed in one basic block
+    (vnd_fir_tmem.cu, compute_main); the only contraction that is harmless is `x * g + 0`.  Checked on the SASS of the built
+    library (cuobjdump ships with the CUDA toolkit the library was built with)."""
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("no cuobjdump")
+    sass = subprocess.run([cuobjdump, "-sass", N.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    functions = re.split(r"\n\s*Function : ", sass)[1:]
+    checked = 0
+    for f in functions:
+        name = f.split("\n", 1)[0]
+        if not re.search(r"fir_|vn_stereo|haas_kernel|place_kernel|stereo_ops", name) or "objective" in name:
+            continue
+        checked += 1
+        bad = [ln.strip() for ln in f.split("\n") if re.search(r"\b[FD]FMA2?\b", ln) and not re.search(r"RZ(\.F32)?\s*;", ln)]
+        assert not bad, f"{name}: contracted multiply-add(s), e.g. {bad[0]}"
+    assert checked >= 10

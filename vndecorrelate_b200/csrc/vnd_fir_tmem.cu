@@ -76,7 +76,7 @@ namespace vnd {
 namespace {
 
 using namespace tm;  // tensor-memory primitives and the tap machinery (vnd_tmem.cuh)
-constexpr int kBarBytes = 256;
+constexpr int kBarBytes = 384;
 
 // Shape of the kernel: G compute warps per lane quarter, each thread owning RG consecutive outputs of its
 // row (a row is R = G * RG outputs), NBUF tile buffers in shared memory, RC / RH registers per compute /
@@ -87,9 +87,20 @@ constexpr int kBarBytes = 256;
 //                        12 warps 279), and every per-tap overhead is spread over 48 outputs instead of 32
 //   <2, 64, 2, 200, 104> 8 compute warps x 64 outputs, rows of 128: TMEM refill 4 instead of 5.33 words per output,
 //                        reach 384; two tile buffers (tile + halo is 74 KB)
-template <int G, int RG, int NBUF, int RC, int RH, bool PIPE = false>
+//   <3, 32, 3, 152, 56, false, true>  round 2: the trailing all-far segment advances together with the first segment
+//                        (pair_first in vnd_tmem.cuh); TMEM is handed over in two column stages
+//   <3, 32, 3, 144, 80, false, false, false, true>  round 2: the lane quarters take their shared-memory phase in two
+//                        alternating groups (kGate, see compute_main)
+template <int G, int RG, int NBUF, int RC, int RH, bool PIPE = false, bool PAIR = false, bool PARK = false, int GATE = 0, int FF = 0>
 struct TmShape {
+  static constexpr bool kFarFirst = FF != 0;   // the trailing all-far segment first (sum parked in the staging row), under the TMEM refill:
+  static constexpr int kFarFirstMode = FF;     // 1: every warp, double-buffered loads; 2: only the last warp of each quarter (two warps
+                                               // per scheduler in the tensor-memory taps at a time), 3: every warp, plain loop
+  static constexpr int kGate = GATE;           // 2: quarters {0, 1} and {2, 3} alternate in the all-far (shared-memory) phase; 4: one quarter at a time
   static constexpr bool kPipe = PIPE;          // tensor-memory taps software-pipelined over two operand buffers
+  static constexpr bool kPair = PAIR;          // first segment and trailing all-far segment in one paired loop
+  static constexpr bool kPark = PARK;          // ... with the far sum parked in the staging row instead of in registers
+  static constexpr int kUnitsA = 7;            // PAIR: the data-movement warp announces the first 7 x 32 TMEM columns separately
   static constexpr int kG = G;                 // compute warps per lane quarter
   static constexpr int kRG = RG;               // outputs per thread
   static constexpr int kR = G * RG;            // outputs per row
@@ -104,12 +115,17 @@ struct TmShape {
   static constexpr int kLaunchRegs = (65536 / kNT) / 8 * 8;
   // mbarrier slots (uint64 each)
   static constexpr int B_IN_FULL = 0, B_IN_FREE = NBUF, B_ST_FULL = 2 * NBUF, B_ST_FREE = 2 * NBUF + 4, B_TM_FULL = 2 * NBUF + 8,
-                       B_TM_FREE = 2 * NBUF + 12, B_COUNT = 2 * NBUF + 16;
+                       B_TM_FREE = 2 * NBUF + 12, B_TM_FULL2 = 2 * NBUF + 16, B_FAR_DONE = 2 * NBUF + 20, B_COUNT = 2 * NBUF + 24;
   static_assert(RG == 32 || RG == 48 || RG == 64, "outputs per thread: one x32, x32 + x16 or x64 tcgen05.ld");
   static_assert(kR % 32 == 0 && ((kPitch / 4) & 1) == 1, "rows are whole 32-column units; the pitch is an odd number of chunks");
   static_assert(32 * (kCW * RC + 4 * RH) <= kLaunchRegs * kNT, "register file");
   static_assert(RC % 8 == 0 && RH % 8 == 0, "setmaxnreg takes multiples of 8");
-  static_assert(B_COUNT * 8 <= 192, "mbarriers");
+  static_assert(B_COUNT * 8 <= 256, "mbarriers");
+  static_assert(GATE == 0 || GATE == 2 || GATE == 4, "far-phase gate");
+  static_assert(!FF || (RG == 32 && !PAIR), "far-first is written for 32 outputs per thread");
+  static_assert(!PAIR || RG == 32, "the paired loop is written for 32 outputs per thread");
+  // Largest tap offset whose columns (up to offset + kR - 1) lie inside the first column stage
+  static constexpr int kStageAMax = 32 * kUnitsA - G * RG;
   // Largest tap offset served from TMEM (every group of a row: group g alone could reach RG (G - 1 - g) samples
   // further, but per-group tap mixes measured slower - 366 instead of 384 Gsamples/s on the same box - because the
   // three warps of a quarter hand TMEM back together and the quarter waits for its slowest group).
@@ -132,8 +148,8 @@ struct TmParams {
   int tiles_per_channel;  // interior tiles
 };
 
-// Dynamic shared memory: [0,192) mbarriers | [192,196) TMEM base | [196,200) first all-far segment |
-//   [256, ...) float in[NBUF][nblk][pitch] | float stage[128][pitch] | int program[] | int ops[G][] | int4 segtab[]
+// Dynamic shared memory: [0,256) mbarriers | [256,260) TMEM base | [260,264) first all-far segment | [264,280) paired-loop plan |
+//   [384, ...) float in[NBUF][nblk][pitch] | float stage[128][pitch] | int program[] | int ops[G][] | int4 segtab[]
 // The role functions rebuild their pointers from this symbol so that every access stays in the
 // shared address space (LDS/STS, not generic loads).
 extern __shared__ __align__(128) unsigned char tm_smem[];
@@ -142,6 +158,7 @@ template <class T>
 struct Smem {
   uint64_t* bars;
   int* s_near_end;  // first segment without a tap in the TMEM window
+  int* s_pair;      // [0] run takes the paired loop, [1] first segment that needs the second column stage, [2] word offset of the last segment's operations
   float* in_all;
   float* stage;
   int* sprog;
@@ -151,7 +168,8 @@ struct Smem {
   int opstride;
   __device__ __forceinline__ explicit Smem(const TmParams& P) {
     bars = reinterpret_cast<uint64_t*>(tm_smem);
-    s_near_end = reinterpret_cast<int*>(tm_smem + 196);
+    s_near_end = reinterpret_cast<int*>(tm_smem + 260);
+    s_pair = reinterpret_cast<int*>(tm_smem + 264);
     in_all = reinterpret_cast<float*>(tm_smem + kBarBytes);
     bufw = (P.nblk * T::kPitch + 31) & ~31;  // TMA tensor copies want 128-byte aligned shared-memory addresses
     stage = in_all + T::kNBuf * bufw;
@@ -210,6 +228,27 @@ __device__ __forceinline__ bool begin_run(const TmParams& P, const Smem<T>& sm, 
       tq += n;
     }
     *sm.s_near_end = ne;
+    if constexpr (T::kPair || T::kFarFirst) {
+      // paired loop: exactly one trailing all-far segment and a first segment served from TMEM only
+      // (far-first only needs the former)
+      const int4 d0 = sm.segtab[0];
+      bool ok = S >= 2 && ne == S - 1 && (T::kFarFirst || ((d0.z & 0xffff) == d0.x && (d0.z >> 16) == d0.y && d0.x + d0.y > 0));
+      int sa = 0, off = 0;  // leading segments whose tensor-memory taps stay inside the first column stage
+      tq = taps;
+      bool in_a = true;
+      for (int s = 0; s < S; ++s) {
+        const int n = sm.sprog[1 + 3 * s] + sm.sprog[2 + 3 * s];
+        if (s == S - 1) off = (int)(tq - taps);
+        for (int k = 0; k < n; ++k)
+          if (tq[k] <= T::kNearMax && tq[k] > T::kStageAMax) in_a = false;
+        if (in_a && s < ne) sa = s + 1;
+        tq += n;
+      }
+      sm.s_pair[0] = ok ? 1 : 0;
+      sm.s_pair[1] = sa;
+      sm.s_pair[2] = off;
+      sm.s_pair[3] = 1;  // see compute_main: the first middle segment, as a run-time value
+    }
   }
   // decode the taps for the thread groups (group g owns outputs RG g .. RG g + RG - 1 of a row)
   for (int t = tid; t < T::kG * (ntaps + 2); t += T::kNT) {
@@ -265,7 +304,7 @@ __device__ __noinline__ void helper_main(const TmParams& P, uint32_t tbase, int 
   for (int run = blockIdx.x; run < n_runs; run += gridDim.x) {
     RunInfo r;
     if (!begin_run<T>(P, sm, run, tid, r)) continue;
-    stagger(q, stagger_ns);
+    if constexpr (T::kGate == 0) stagger(q, stagger_ns);
     int load_row = r.first_tile * kRows;  // first row (R samples) of the next tile to load
     int store_row = r.first_tile * kRows + 32 * q;
     int to_load = r.n_tiles;
@@ -308,6 +347,14 @@ __device__ __noinline__ void helper_main(const TmParams& P, uint32_t tbase, int 
             sub = 0;
             src += 1;
           }
+          if constexpr (T::kPair) {
+            if (k32 == T::kUnitsA - 1) {  // the first column stage is complete: the quarter may start its first segments
+              tmem_wait_st();
+              tmem_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_u32(bars + 8u * (T::B_TM_FULL + q));
+            }
+          }
         }
         tmem_wait_st();
       }
@@ -315,7 +362,7 @@ __device__ __noinline__ void helper_main(const TmParams& P, uint32_t tbase, int 
       __syncwarp();
       VND_TRACE(ti, 1);
       if (lane == 0) {
-        mbar_arrive_u32(bars + 8u * (T::B_TM_FULL + q));
+        mbar_arrive_u32(bars + 8u * ((T::kPair ? T::B_TM_FULL2 : T::B_TM_FULL) + q));
         mbar_arrive_u32(bars + 8u * (T::B_IN_FREE + fb));
       }
       if (++fb == T::kNBuf) {
@@ -362,33 +409,163 @@ __device__ __noinline__ void compute_main(const TmParams& P, uint32_t tbase, int
   int b = 0;           // ring slot of the current tile
   unsigned fpar = 0;   // in_full parity of slot b
   unsigned tpar = 0;   // parity of the tile counter (TMEM and staging barriers)
+  bool first_tile = true;  // kGate: no far phase of the other group precedes the very first tile
   for (int run = blockIdx.x; run < n_runs; run += gridDim.x) {
     RunInfo r;
     if (!begin_run<T>(P, sm, run, tid, r)) continue;
-    stagger(q, stagger_ns);
+    if constexpr (T::kGate == 0) stagger(q, stagger_ns);
     const int S = sm.sprog[0];
     const int near_end = *sm.s_near_end;
+    const bool pair_ok = (T::kPair || T::kFarFirst) && sm.s_pair[0] != 0 && (T::kFarFirstMode != 2 || g == T::kG - 1);
+    const int stage_a = T::kPair ? sm.s_pair[1] : 0;
+    const int* ops_far = sm.ops + g * sm.opstride + ((T::kPair || T::kFarFirst) ? sm.s_pair[2] : 0);
+    // Always 1, but read from shared memory: with a constant, run_segments loses its `s == 0` branch, the segment's
+    // multiply and the add into the running output land in one basic block, and ptxas contracts the two packed
+    // operations into FFMA2 (one rounding instead of two) although both carry .rn and the build says -fmad=false.
+    // tests/test_host_logic.py checks the SASS of the FIR kernels for such contractions.
+    const int seg1 = T::kPair ? sm.s_pair[3] : 1;
     for (int ti = 0; ti < r.n_tiles; ++ti) {
       const uint32_t row = smem_u32(sm.in_all + b * sm.bufw + m * T::kPitch);
-      float yv[RG];
-#pragma unroll
-      for (int rr = 0; rr < RG; ++rr) yv[rr] = 0.0f;
       const int* ops = sm.ops + g * sm.opstride;
       VND_TRACE(ti, 0);
       mbar_wait(&bars[T::B_IN_FULL + b], fpar);
+      bool staged_wait = false;
+      // kGate: the phase that loads the shared-memory pipe (the all-far segments, next to the TMEM refill) is taken in turns.
+      // Left alone, the four quarters fall into step (tools/trace_tmem.py): the pipe saturates while all of them are in that
+      // phase and idles during the tensor-memory phase.  kGate == 2: quarters {0, 1} and {2, 3} alternate - group 1 enters
+      // the far phase of its n-th tile when group 0 has finished that of its n-th tile, group 0 that of tile n + 1 when
+      // group 1 has finished tile n.  kGate == 4: a ring, one quarter at a time.
+      auto gate_enter = [&]() {
+        if constexpr (T::kGate == 2) {
+          if (q < 2) {
+            if (!first_tile) mbar_wait(&bars[T::B_FAR_DONE + 1], tpar ^ 1u);
+          } else {
+            mbar_wait(&bars[T::B_FAR_DONE + 0], tpar);
+          }
+        } else if constexpr (T::kGate == 4) {
+          if (q == 0) {
+            if (!first_tile) mbar_wait(&bars[T::B_FAR_DONE + 3], tpar ^ 1u);
+          } else {
+            mbar_wait(&bars[T::B_FAR_DONE + q - 1], tpar);
+          }
+        }
+      };
+      auto gate_leave = [&]() {
+        if constexpr (T::kGate != 0) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[T::B_FAR_DONE + (T::kGate == 2 ? (q >> 1) : q)]);
+          first_tile = false;
+        }
+      };
+      if constexpr (T::kFarFirst) {
+        if (pair_ok) {
+          // The trailing all-far segment first: it only needs the staged tile, so it runs while the data-movement warp
+          // still refills the quarter's TMEM rows; its scaled sum waits in the thread's slot of the staging row.
+          float far[RG];
+          gate_enter();
+          if constexpr (T::kFarFirstMode == 1) {
+            far_first(segtab, S, ops_far, row, far);
+          } else {  // the plain far loop on a zeroed accumulator: 0 + acc * gain (the running output is never -0, so
+                    // adding +0 instead of -0 later cannot change it)
+#pragma unroll
+            for (int rr = 0; rr < RG; ++rr) far[rr] = 0.0f;
+            const int* of = ops_far;
+            run_segments<true, false>(segtab, S - 1, S, of, tcol0, row, far);
+          }
+          gate_leave();
+          mbar_wait(&bars[T::B_ST_FREE + q], tpar ^ 1u);  // the previous tile's store has read the staging rows
+          staged_wait = true;
+          float4* park = reinterpret_cast<float4*>(sm.stage + m * T::kPitch + RG * g);
+#pragma unroll
+          for (int jj = 0; jj < RG / 4; ++jj) park[jj] = make_float4(far[4 * jj], far[4 * jj + 1], far[4 * jj + 2], far[4 * jj + 3]);
+          VND_TRACE(ti, 6);
+        }
+      }
+      float yv[RG];  // (zeroed only here: live zeros across the far-first loop cost 32 registers)
+#pragma unroll
+      for (int rr = 0; rr < RG; ++rr) yv[rr] = 0.0f;
       mbar_wait(&bars[T::B_TM_FULL + q], tpar);
       tmem_fence_after();
       VND_TRACE(ti, 1);
-      run_segments<false, T::kPipe>(segtab, 0, near_end, ops, tcol0, row, yv);
-      VND_TRACE(ti, 2);
-      tmem_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[T::B_TM_FREE + q]);  // the helper may fill TMEM for the next tile
-      run_segments<true, false>(segtab, near_end, S, ops, tcol0, row, yv);
+      if constexpr (T::kFarFirst) {
+        if (pair_ok) {
+          run_segments<false, false>(segtab, 0, near_end, ops, tcol0, row, yv);
+          VND_TRACE(ti, 2);
+          tmem_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[T::B_TM_FREE + q]);  // the helper may fill TMEM for the next tile
+          const float4* park = reinterpret_cast<const float4*>(sm.stage + m * T::kPitch + RG * g);
+#pragma unroll
+          for (int jj = 0; jj < RG / 4; ++jj) {
+            const float4 v = park[jj];
+            add2(yv[4 * jj], yv[4 * jj + 1], v.x, v.y);
+            add2(yv[4 * jj + 2], yv[4 * jj + 3], v.z, v.w);
+          }
+        }
+      }
+      if constexpr (T::kPair) {
+        if (pair_ok) {
+          // Segment 0 and the trailing all-far segment together (vnd_tmem.cuh: pair_first), then the middle segments; the
+          // far sum is added last, as in the reference.
+          if (stage_a < 1) {
+            mbar_wait(&bars[T::B_TM_FULL2 + q], tpar);
+            tmem_fence_after();
+          }
+          float far[RG];
+          pair_first(segtab, S, ops, ops_far, tcol0, row, yv, far);
+          VND_TRACE(ti, 6);
+          float4* park = reinterpret_cast<float4*>(sm.stage + m * T::kPitch + RG * g);
+          if constexpr (T::kPark) {
+            mbar_wait(&bars[T::B_ST_FREE + q], tpar ^ 1u);  // the previous tile's store has read the staging rows
+            staged_wait = true;
+#pragma unroll
+            for (int jj = 0; jj < RG / 4; ++jj) park[jj] = make_float4(far[4 * jj], far[4 * jj + 1], far[4 * jj + 2], far[4 * jj + 3]);
+          }
+          const int* ops1 = ops + segtab[0].x + segtab[0].y;
+          const int s_mid = stage_a < 1 ? 1 : (stage_a < near_end ? stage_a : near_end);
+          run_segments<false, false>(segtab, seg1, s_mid, ops1, tcol0, row, yv);
+          if (stage_a >= 1) {
+            mbar_wait(&bars[T::B_TM_FULL2 + q], tpar);
+            tmem_fence_after();
+          }
+          VND_TRACE(ti, 7);
+          run_segments<false, false>(segtab, s_mid, near_end, ops1, tcol0, row, yv);
+          VND_TRACE(ti, 2);
+          tmem_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[T::B_TM_FREE + q]);  // the helper may fill TMEM for the next tile
+          if constexpr (T::kPark) {
+#pragma unroll
+            for (int jj = 0; jj < RG / 4; ++jj) {
+              const float4 v = park[jj];
+              far[4 * jj] = v.x;
+              far[4 * jj + 1] = v.y;
+              far[4 * jj + 2] = v.z;
+              far[4 * jj + 3] = v.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < RG / 2; ++j) add2(yv[2 * j], yv[2 * j + 1], far[2 * j], far[2 * j + 1]);
+        } else {
+          mbar_wait(&bars[T::B_TM_FULL2 + q], tpar);
+          tmem_fence_after();
+        }
+      }
+      if (!(T::kPair || T::kFarFirst) || !pair_ok) {
+        run_segments<false, T::kPipe>(segtab, 0, near_end, ops, tcol0, row, yv);
+        VND_TRACE(ti, 2);
+        tmem_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[T::B_TM_FREE + q]);  // the helper may fill TMEM for the next tile
+        gate_enter();
+        VND_TRACE(ti, 6);
+        run_segments<true, false>(segtab, near_end, S, ops, tcol0, row, yv);
+        gate_leave();
+      }
       VND_TRACE(ti, 3);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[T::B_IN_FREE + b]);  // this warp is done with the tile buffer
-      mbar_wait(&bars[T::B_ST_FREE + q], tpar ^ 1u);
+      if (!staged_wait) mbar_wait(&bars[T::B_ST_FREE + q], tpar ^ 1u);
       VND_TRACE(ti, 5);  // the previous tile's stores have read the staging rows
       {
         float4* dst = reinterpret_cast<float4*>(sm.stage + m * T::kPitch + RG * g);
@@ -411,7 +588,7 @@ __device__ __noinline__ void compute_main(const TmParams& P, uint32_t tbase, int
 template <class T>
 __global__ void __launch_bounds__(T::kNT, 1) fir_tmem_kernel(const __grid_constant__ TmParams P) {
   const Smem<T> sm(P);
-  uint32_t* tm_slot = reinterpret_cast<uint32_t*>(tm_smem + 192);
+  uint32_t* tm_slot = reinterpret_cast<uint32_t*>(tm_smem + 256);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -425,7 +602,9 @@ __global__ void __launch_bounds__(T::kNT, 1) fir_tmem_kernel(const __grid_consta
       mbar_init(&sm.bars[T::B_ST_FREE + k], 1);
       mbar_init(&sm.bars[T::B_TM_FULL + k], 1);
       mbar_init(&sm.bars[T::B_TM_FREE + k], T::kG);
+      mbar_init(&sm.bars[T::B_TM_FULL2 + k], 1);
     }
+    for (int k = 0; k < 4; ++k) mbar_init(&sm.bars[T::B_FAR_DONE + k], T::kGate == 2 ? 2 * T::kG : T::kG);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc_all(tm_slot);
@@ -561,12 +740,33 @@ static int fir_tmem_launch_t(const FirParams& f, int max_prog_words, cudaStream_
 // Two compute warps per scheduler do not make the tensor-memory path faster in the kernel (they do in
 // tools/microbench/tmem_lat.cu), and a second tcgen05.ld in flight per warp slows the taps down even with the
 // intended instruction order, so the round-1 shape stays.
+// Scheduling variants of the default shape (third session of round 2, same measurement, default 378-380; the timelines
+// behind the verdicts are in profiles/r02_summary.md):
+//   5: trailing all-far segment paired tap by tap with the first segment (pair_first), far sum parked           278
+//      (full-width steps spilled scalars into the hot loops: 203 at 144 registers, 277 at 152)
+//   6: quarters {0,1} / {2,3} alternate in the far phase (kGate 2)                                                 375
+//   7: one quarter at a time in the far phase (kGate 4, a ring)                                                    268
+//   8: all-far segment first with double-buffered loads, sum parked (kFarFirstMode 1)                              321
+//   9 / 10: 8 with kGate 2 / 4                                                                                      306 / 219
+//   11: all-far segment first on the last warp of each quarter only (two warps per scheduler in TMEM taps)        307
+//   12: all-far segment first on every warp, plain loop                                                            344
+// The per-warp chain of a tap (~240 clk from tensor memory, ~400 clk from shared memory) does not shorten when fewer
+// warps contend (far phase 3.2 k clk per tile with one quarter in it, 3.5 k with two, 3.8 k with four), so taking turns
+// buys nothing, and every form of overlap inside a warp has made the taps slower.
 int fir_tmem_launch(const FirParams& f, int max_prog_words, cudaStream_t st, long long* frames_done) {
   switch (g_tm_shape) {
     case 1: return fir_tmem_launch_t<TmShape<2, 48, 3, 200, 104>>(f, max_prog_words, st, frames_done);
     case 2: return fir_tmem_launch_t<TmShape<2, 64, 2, 216, 72>>(f, max_prog_words, st, frames_done);
     case 3: return fir_tmem_launch_t<TmShape<2, 32, 3, 200, 104>>(f, max_prog_words, st, frames_done);
     case 4: return fir_tmem_launch_t<TmShape<2, 32, 3, 200, 104, true>>(f, max_prog_words, st, frames_done);
+    case 5: return fir_tmem_launch_t<TmShape<3, 32, 3, 144, 80, false, true, true>>(f, max_prog_words, st, frames_done);
+    case 6: return fir_tmem_launch_t<TmShape<3, 32, 3, 144, 80, false, false, false, 2>>(f, max_prog_words, st, frames_done);
+    case 7: return fir_tmem_launch_t<TmShape<3, 32, 3, 144, 80, false, false, false, 4>>(f, max_prog_words, st, frames_done);
+    case 8: return fir_tmem_launch_t<TmShape<3, 32, 3, 144, 80, false, false, false, 0, 1>>(f, max_prog_words, st, frames_done);
+    case 9: return fir_tmem_launch_t<TmShape<3, 32, 3, 144, 80, false, false, false, 2, 1>>(f, max_prog_words, st, frames_done);
+    case 10: return fir_tmem_launch_t<TmShape<3, 32, 3, 144, 80, false, false, false, 4, 1>>(f, max_prog_words, st, frames_done);
+    case 11: return fir_tmem_launch_t<TmShape<3, 32, 3, 144, 80, false, false, false, 0, 2>>(f, max_prog_words, st, frames_done);
+    case 12: return fir_tmem_launch_t<TmShape<3, 32, 3, 144, 80, false, false, false, 0, 3>>(f, max_prog_words, st, frames_done);
     default: return fir_tmem_launch_t<TmShape<3, 32, 3, 144, 80>>(f, max_prog_words, st, frames_done);
   }
 }

@@ -110,6 +110,20 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// One poll of an mbarrier phase (no blocking, no sleep).
+__device__ __forceinline__ bool mbar_try_u32(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
                "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
@@ -210,6 +224,53 @@ __device__ __forceinline__ void far_tap_a(uint32_t row, int op, float (&acc)[RG]
   } else {  // odd shift: the pairs of the loaded data straddle the accumulator pairs -> scalar adds
 #pragma unroll
     for (int r = 0; r < RG; ++r) acc[r] = SUB ? fsub(acc[r], t[r + A]) : fadd(acc[r], t[r + A]);
+  }
+}
+
+// The same tap in two steps, for the paired loop below: the nine (eight when A == 0) 16-byte loads first, the adds once
+// something else has been issued behind them.
+__device__ __forceinline__ void far_load9(uint32_t row, int op, float4 (&c)[9]) {
+  const uint32_t p = row + 4u * (uint32_t)(op & 0xffff);
+  const int kx = (op >> 16) & 31;
+  if (kx >= 9) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c[k] = lds128(p + 16u * k);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c[k] = lds128(p + 16u * k + (k < kx ? 0u : 16u));
+  }
+  if ((op >> 24) & 3) c[8] = lds128(p + 128u + (8 < kx ? 0u : 16u));  // the ninth chunk only exists for an unaligned tap
+  else c[8] = c[7];
+}
+template <int A, bool SUB, int RG>
+__device__ __forceinline__ void far_add9(const float4 (&c)[9], float (&acc)[RG]) {
+  static_assert(RG == 32, "nine chunks hold 32 operands");
+  float t[36];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    t[4 * k] = c[k].x;
+    t[4 * k + 1] = c[k].y;
+    t[4 * k + 2] = c[k].z;
+    t[4 * k + 3] = c[k].w;
+  }
+  if constexpr (A % 2 == 0) {
+#pragma unroll
+    for (int j = 0; j < RG / 2; ++j) {
+      if constexpr (SUB) sub2(acc[2 * j], acc[2 * j + 1], t[2 * j + A], t[2 * j + 1 + A]);
+      else add2(acc[2 * j], acc[2 * j + 1], t[2 * j + A], t[2 * j + 1 + A]);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < RG; ++r) acc[r] = SUB ? fsub(acc[r], t[r + A]) : fadd(acc[r], t[r + A]);
+  }
+}
+template <bool SUB, int RG>
+__device__ __forceinline__ void far_add9_any(const float4 (&c)[9], int op, float (&acc)[RG]) {
+  switch ((op >> 24) & 3) {
+    case 0: far_add9<0, SUB>(c, acc); break;
+    case 1: far_add9<1, SUB>(c, acc); break;
+    case 2: far_add9<2, SUB>(c, acc); break;
+    default: far_add9<3, SUB>(c, acc); break;
   }
 }
 
@@ -349,6 +410,171 @@ __device__ __forceinline__ void run_segments(const int4* __restrict__ segtab, in
       for (int j = 0; j < RG / 2; ++j) add2(yv[2 * j], yv[2 * j + 1], acc[2 * j], acc[2 * j + 1]);
     }
   }
+}
+
+// ---- paired first step (TmShape::kPair) ------------------------------------------------------------
+// The decay segments are independent sums (decorrelation.py:402-414: `acc` restarts per segment); only the running
+// output adds them in order.  So the trailing all-far segment need not wait for the tensor-memory segments: here it
+// advances together with the FIRST segment, one tap of each per step - the nine shared-memory loads of the far tap
+// are issued, a tensor-memory tap runs behind them, then the far tap's adds - while the running output is not live
+// yet (its registers hold the second accumulator).  The far sum is scaled, kept, and added last, so every output
+// sees the reference's operations in the reference's order.
+// One half of a paired step: outputs [16 H, 16 H + 16) of the thread.  The far tap's operands for that half lie in
+// chunks 4 H .. 4 H + 4 of its nine (the fifth only for an unaligned tap); the tensor-memory tap reads 16 columns.
+// Halves keep the loop at ~100 live registers (two 32-float accumulators, 16 + 20 landing registers): the full-width
+// version (36 + 32 landing registers) spilled scalars into the hot loops and ran at 277 instead of 378 Gsamples/s.
+template <int H, bool SUBF, int A>
+__device__ __forceinline__ void far_add_half(const float4 (&c)[5], float (&far)[32]) {
+  float t[20];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    t[4 * k] = c[k].x;
+    t[4 * k + 1] = c[k].y;
+    t[4 * k + 2] = c[k].z;
+    t[4 * k + 3] = c[k].w;
+  }
+  if constexpr (A % 2 == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if constexpr (SUBF) sub2(far[16 * H + 2 * j], far[16 * H + 2 * j + 1], t[2 * j + A], t[2 * j + 1 + A]);
+      else add2(far[16 * H + 2 * j], far[16 * H + 2 * j + 1], t[2 * j + A], t[2 * j + 1 + A]);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) far[16 * H + r] = SUBF ? fsub(far[16 * H + r], t[r + A]) : fadd(far[16 * H + r], t[r + A]);
+  }
+}
+template <int H>
+__device__ __forceinline__ void pair_half(int opn, int opf, bool subn, bool subf, uint32_t tcol0, uint32_t row, float (&acc)[32], float (&far)[32]) {
+  const uint32_t p = row + 4u * (uint32_t)(opf & 0xffff);
+  const int kx = (opf >> 16) & 31, A = (opf >> 24) & 3;
+  float4 c[5];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) c[k] = lds128(p + 16u * (4 * H + k) + ((4 * H + k) < kx ? 0u : 16u));
+  if (A) c[4] = lds128(p + 16u * (4 * H + 4) + ((4 * H + 4) < kx ? 0u : 16u));
+  else c[4] = c[3];
+  {
+    float t[16];
+    tmem_ld<16, 0>(t, tcol0 + (uint32_t)opn + 16u * H);
+    tmem_wait_ld(t);
+    if (subn) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sub2(acc[16 * H + 2 * j], acc[16 * H + 2 * j + 1], t[2 * j], t[2 * j + 1]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) add2(acc[16 * H + 2 * j], acc[16 * H + 2 * j + 1], t[2 * j], t[2 * j + 1]);
+    }
+  }
+  if (subf) {
+    switch (A) {
+      case 0: far_add_half<H, true, 0>(c, far); break;
+      case 1: far_add_half<H, true, 1>(c, far); break;
+      case 2: far_add_half<H, true, 2>(c, far); break;
+      default: far_add_half<H, true, 3>(c, far); break;
+    }
+  } else {
+    switch (A) {
+      case 0: far_add_half<H, false, 0>(c, far); break;
+      case 1: far_add_half<H, false, 1>(c, far); break;
+      case 2: far_add_half<H, false, 2>(c, far); break;
+      default: far_add_half<H, false, 3>(c, far); break;
+    }
+  }
+}
+template <int RG>
+__device__ __forceinline__ void pair_step(int opn, int opf, bool subn, bool subf, uint32_t tcol0, uint32_t row, float (&acc)[RG], float (&far)[RG]) {
+  static_assert(RG == 32, "two halves of 16 outputs");
+  pair_half<0>(opn, opf, subn, subf, tcol0, row, acc, far);
+  pair_half<1>(opn, opf, subn, subf, tcol0, row, acc, far);
+}
+
+// Segment 0 (every tap inside the TMEM window) into yv, segment S - 1 (no tap inside it) scaled into far.
+// ops: decoded operations of segment 0 (those of the later segments follow), opsF: those of segment S - 1.
+template <int RG>
+__device__ __forceinline__ void pair_first(const int4* __restrict__ segtab, int S, const int* __restrict__ ops, const int* __restrict__ opsF,
+                                           uint32_t tcol0, uint32_t row, float (&yv)[RG], float (&far)[RG]) {
+  const int4 d0 = segtab[0], dF = segtab[S - 1];
+  const int nneg0 = d0.x, n0 = d0.x + d0.y, nnegF = dF.x, nF = dF.x + dF.y;
+  const int np = n0 < nF ? n0 : nF;
+  float acc[RG];
+#pragma unroll
+  for (int r = 0; r < RG; ++r) {
+    acc[r] = 0.0f;
+    far[r] = 0.0f;
+  }
+  int k = 0;
+  if (np > 0) {  // unrolled by two with the operation words in alternating registers (see tap_list)
+    int na = ops[0], fa = opsF[0];
+    for (;;) {
+      const int nb = ops[k + 1], fb = opsF[k + 1];  // slack words follow the lists
+      pair_step(na, fa, k < nneg0, k < nnegF, tcol0, row, acc, far);
+      if (++k >= np) break;
+      na = ops[k + 1];
+      fa = opsF[k + 1];
+      pair_step(nb, fb, k < nneg0, k < nnegF, tcol0, row, acc, far);
+      if (++k >= np) break;
+    }
+  }
+  for (int j = k; j < n0; ++j) {  // the first segment has more taps than the far one
+    float t[RG];
+    near_issue(t, tcol0 + (uint32_t)ops[j]);
+    tmem_wait_ld(t);
+    if (j < nneg0) near_add<true>(t, acc);
+    else near_add<false>(t, acc);
+  }
+  {
+    const float g0 = __int_as_float(d0.w);
+#pragma unroll
+    for (int j = 0; j < RG / 2; ++j) {
+      mul2(acc[2 * j], acc[2 * j + 1], g0, g0);
+      yv[2 * j] = acc[2 * j];
+      yv[2 * j + 1] = acc[2 * j + 1];
+      add2(yv[2 * j], yv[2 * j + 1], 0.0f, 0.0f);  // the reference adds into zeros
+    }
+  }
+  for (int j = k; j < nF; ++j) {  // ... or fewer
+    if (j < nnegF) far_tap<true>(row, opsF[j], far);
+    else far_tap<false>(row, opsF[j], far);
+  }
+  {
+    const float gF = __int_as_float(dF.w);
+#pragma unroll
+    for (int j = 0; j < RG / 2; ++j) mul2(far[2 * j], far[2 * j + 1], gF, gF);
+  }
+}
+
+// ---- far-first (TmShape::kFarFirst) ------------------------------------------------------------------
+// The trailing all-far segment alone, before anything else of the tile: the running output is not live yet, so two
+// landing buffers fit and the nine loads of tap k + 1 are in flight under the adds of tap k.  Scaled sum into far.
+template <int RG>
+__device__ __forceinline__ void far_first(const int4* __restrict__ segtab, int S, const int* __restrict__ opsF, uint32_t row, float (&far)[RG]) {
+  const int4 dF = segtab[S - 1];
+  const int nneg = dF.x, n = dF.x + dF.y;
+#pragma unroll
+  for (int r = 0; r < RG; ++r) far[r] = 0.0f;
+  if (n > 0) {
+    float4 ca[9], cb[9];
+    int oa = opsF[0];
+    far_load9(row, oa, ca);
+    int k = 0;
+    for (;;) {
+      // (the prefetch behind the last tap reads the zero slack word that follows the list: nine loads from the start
+      // of the thread's row, unused - cheaper than a conditional load, whose two definitions cost registers)
+      const int ob = opsF[k + 1];
+      far_load9(row, ob, cb);
+      if (k < nneg) far_add9_any<true>(ca, oa, far);
+      else far_add9_any<false>(ca, oa, far);
+      if (++k >= n) break;
+      oa = opsF[k + 1];
+      far_load9(row, oa, ca);
+      if (k < nneg) far_add9_any<true>(cb, ob, far);
+      else far_add9_any<false>(cb, ob, far);
+      if (++k >= n) break;
+    }
+  }
+  const float gF = __int_as_float(dF.w);
+#pragma unroll
+  for (int j = 0; j < RG / 2; ++j) mul2(far[2 * j], far[2 * j + 1], gF, gF);
 }
 
 }  // namespace tm
