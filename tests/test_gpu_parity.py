@@ -9,6 +9,8 @@ scores, whose tolerance is written next to each assertion.  Needs a CUDA device:
 
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -404,6 +406,41 @@ def test_planar_slab_tmem_kernel(api, frames, kappa, envelope, duration):
     if not G.same_bits(got, want):
         bad = np.argwhere(got.view(np.uint32) != want.view(np.uint32))
         raise AssertionError(f"{len(bad)} samples differ; first at (frame, channel) {bad[0]}, last {bad[-1]}")
+
+
+@pytest.mark.parametrize("shape", list(range(1, 13)))
+def test_tmem_kernel_variants_are_bit_exact(api, shape):
+    """Every measured variant of the tensor-memory kernel (shapes, software pipelining, paired first / far segments,
+    alternating far phases, far-first; vnd_fir_tmem.cu: fir_tmem_launch) must produce the default kernel's - the oracle's -
+    bits: the reference's operations in the reference's order, however the work is scheduled.  Three programs: the
+    BASELINE shape of filter, uniform impulses (most taps outside the TMEM window, no paired loop) and a two-segment
+    envelope with a negative gain."""
+    import torch
+
+    from vndecorrelate_b200 import _native as N
+
+    lib = N.lib()
+    lib.vnd_debug_set_tm_shape.argtypes = [C.c_int]
+    lib.vnd_debug_set_tm_shape.restype = C.c_int
+    Cn = 5
+    filtered = (0, 1, 2, 3)
+    prev = lib.vnd_debug_set_tm_shape(shape)
+    try:
+        for kappa, envelope, frames in ((1.0, (0.85, 0.55, 0.35, 0.2), 190001), (0.0, (0.85, 0.55, 0.35, 0.2), 170003), (1.0, (0.9, -0.5), 160000)):
+            vn = api.VelvetNoise(sample_rate_hz=48000, duration_seconds=0.03, num_impulses=30, num_outs=Cn, filtered_channels=filtered, mode="LR",
+                                 normalizer=None, log_distribution_strength=kappa, segment_envelope=envelope, seed=11)
+            g = torch.Generator(device="cuda").manual_seed(7 + shape)
+            slab = torch.randn((Cn, frames), generator=g, device="cuda") * 0.1
+            y = vn.convolve(slab.t())
+            taps = O.class_taps(sample_rate_hz=48000, duration_seconds=0.03, num_impulses=30, num_outs=Cn, filtered_channels=filtered,
+                                num_segments=len(envelope), log_distribution_strength=kappa, seed=11)
+            want = O.fir_class_order(np.ascontiguousarray(slab.cpu().numpy().T), taps, envelope, Cn)
+            got = np.ascontiguousarray(y.cpu().numpy())
+            if not G.same_bits(got, want):
+                bad = np.argwhere(got.view(np.uint32) != want.view(np.uint32))
+                raise AssertionError(f"shape {shape}, strength {kappa}: {len(bad)} samples differ; first at (frame, channel) {bad[0]}")
+    finally:
+        lib.vnd_debug_set_tm_shape(prev)
 
 
 def test_planar_slab_unaligned_falls_back(api):

@@ -631,11 +631,19 @@ static const int g_stagger_ns = [] {
   const char* e = getenv("VND_TM_STAGGER_NS");
   return e ? atoi(e) : 2000;
 }();
-// VND_TM_SHAPE picks the kernel shape (see TmShape and fir_tmem_launch): 0 = 3 x 32 (default), 1 = 2 x 48, 2 = 2 x 64, 3 = 2 x 32, 4 = 3 pipelined.
-static const int g_tm_shape = [] {
+// VND_TM_SHAPE picks the kernel variant (see TmShape and fir_tmem_launch): 0 = 3 x 32 (default), 1 = 2 x 48, 2 = 2 x 64, 3 = 2 x 32,
+// 4 = 3 pipelined, 5-12 = scheduling variants of the default shape.
+static int g_tm_shape = [] {
   const char* e = getenv("VND_TM_SHAPE");
   return e ? atoi(e) : VND_TM_DEFAULT_SHAPE;
 }();
+// Debug / test aid (not part of the ABI in include/vnd_b200.h): select the kernel variant at run time so that the
+// parity tests can exercise every measured variant in one process; returns the previous selection.  Not thread-safe.
+extern "C" int vnd_debug_set_tm_shape(int shape) {
+  const int prev = g_tm_shape;
+  g_tm_shape = shape;
+  return prev;
+}
 
 // cuTensorMapEncodeTiled through the runtime (no link against libcuda).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
