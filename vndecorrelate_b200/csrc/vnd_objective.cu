@@ -277,6 +277,81 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
+// The float64 pipe is what bounds this kernel (one atan2, one sqrt and the moments per frame and delay; the clip itself
+// stays in L2 across its delays), so both functions are written out lean instead of calling the library versions with
+// their special-case paths: ~45 instead of ~100 float64 instructions per frame.
+//
+// Folded angle (utils/dsp.py:399-412): atan2(d, s) brought into [-pi/2, pi/2] by adding or subtracting pi is atan(d / s)
+// with the sign of d * s (sign of d alone for s == 0, 0 for d == s == 0).  |d| / |s| is reduced to |t| <= tan(pi/16) with
+// one of the base angles 0, pi/8, pi/4 (after swapping so that the ratio is <= 1): atan(a / b) = base + atan((a - c b) /
+// (b + c a)), c = tan(base); ten Taylor terms then leave < 1e-16.  The base is picked from float32 copies of a and b (any
+// choice near a threshold is fine).  Explicit fma() throughout: nothing here is pinned to numpy's rounding (scores are
+// compared at 1e-9), unlike the float32 paths of this library.
+__device__ __forceinline__ double rcp_lean(double x) {  // x > 0, normal
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
+__device__ __forceinline__ double sqrt_lean(double x) {  // x >= 0
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double hx = 0.5 * x;
+  r = fma(r, fma(-hx * r, r, 0.5), r);
+  r = fma(r, fma(-hx * r, r, 0.5), r);
+  return x > 0.0 ? x * r : 0.0;
+}
+__device__ __forceinline__ double abs_bits(double x) { return __hiloint2double(__double2hiint(x) & 0x7fffffff, __double2loint(x)); }
+// d, s: the float64 difference and sum of the two channels; df, sf: float32 copies of them, only used to pick the
+// reduction (which operand is larger, which base angle): any choice near a threshold is fine.
+__device__ __forceinline__ double folded_angle(double d, double s, float df, float sf) {
+  const double kC1 = 0.41421356237309503;  // tan(pi/8)
+  const float fa = fabsf(df), fb = fabsf(sf);
+  const bool inv = fa > fb;  // atan(a / b) = pi/2 - atan(b / a)
+  const double ad = abs_bits(d), as = abs_bits(s);
+  const double a = inv ? as : ad, b = inv ? ad : as;
+  const float af = inv ? fb : fa, bf = inv ? fa : fb;
+  const bool k1 = af > 0.19891237f * bf, k2 = af > 0.66817864f * bf;  // tan(pi/16), tan(3 pi/16)
+  const double c = k2 ? 1.0 : (k1 ? kC1 : 0.0);
+  const double base = k2 ? 0.7853981633974483 : (k1 ? 0.39269908169872414 : 0.0);
+  const double num = fma(-c, b, a), den = fma(c, a, b);
+  const double t = den > 0.0 ? num * rcp_lean(den) : 0.0;
+  const double z = t * t;
+  double p = -1.0 / 19.0;
+  p = fma(p, z, 1.0 / 17.0);
+  p = fma(p, z, -1.0 / 15.0);
+  p = fma(p, z, 1.0 / 13.0);
+  p = fma(p, z, -1.0 / 11.0);
+  p = fma(p, z, 1.0 / 9.0);
+  p = fma(p, z, -1.0 / 7.0);
+  p = fma(p, z, 1.0 / 5.0);
+  p = fma(p, z, -1.0 / 3.0);
+  double th = base + fma(t * z, p, t);
+  if (inv) th = 1.5707963267948966 - th;
+  // sign of d * s (s == +-0 counts as positive: atan2(d, +-0) = sign(d) * pi/2)
+  const int neg = (__double2hiint(d) ^ (s < 0.0 ? 0x80000000 : 0)) & 0x80000000;
+  return __hiloint2double(__double2hiint(th) ^ neg, __double2loint(th));
+}
+
+struct HaasAcc {
+  double v0 = 0, v1 = 0, v2 = 0, v3 = 0, v5 = 0, v6 = 0;
+  long long vmax = 0;  // bits of max |theta| (non-negative doubles order like integers)
+  __device__ __forceinline__ void add(double l, double r, float lf, float rf) {
+    const double th = folded_angle(l - r, l + r, lf - rf, lf + rf);
+    const double rad = sqrt_lean(fma(l, l, r * r));
+    const double rt = rad * th, t2 = th * th;
+    v0 += rad;
+    v1 += rt;
+    v2 = fma(rad, t2, v2);
+    v3 = fma(rt, t2, v3);
+    const long long ab = __double_as_longlong(th) & 0x7fffffffffffffffLL;
+    vmax = ab > vmax ? ab : vmax;
+    v5 = fma(l, r, v5);
+    v6 = fma(l, l, v6);
+  }
+};
+
 template <typename TIn>
 __global__ void __launch_bounds__(256) haas_objective_kernel(const TIn* __restrict__ clips, long long frames, long long clip_stride,
                                                              long long chan_stride, const int* __restrict__ delays, int n_cand,
@@ -286,23 +361,29 @@ __global__ void __launch_bounds__(256) haas_objective_kernel(const TIn* __restri
   const TIn* __restrict__ x0 = clips + (long long)clip * clip_stride;
   const TIn* __restrict__ x1 = x0 + chan_stride;
   const long long total = frames + d;
-  const double kHalfPi = 1.5707963267948966, kPi = 3.141592653589793;
-  double v[7] = {0, 0, 0, 0, 0, 0, 0};
-  for (long long m = threadIdx.x; m < total; m += blockDim.x) {
-    const double l = (m >= d) ? (double)x0[m - d] : 0.0;  // channel 0 delayed (decorrelation.py:220-222)
-    const double r = (m < frames) ? (double)x1[m] : 0.0;
-    double th = atan2(l - r, l + r);
-    if (th < -kHalfPi) th += kPi;
-    else if (th > kHalfPi) th -= kPi;
-    const double rad = sqrt(l * l + r * r);
-    v[0] += rad;
-    v[1] += rad * th;
-    v[2] += rad * (th * th);
-    v[3] += rad * (th * th * th);
-    v[4] = fmax(v[4], fabs(th));
-    v[5] += l * r;
-    v[6] += l * l;
+  HaasAcc acc;
+  // Three stretches (decorrelation.py:220-222: channel 0 delayed by d, both padded to frames + d): only channel 1 for
+  // m < d, both channels for d <= m < frames, only the delayed channel 0 behind the end of channel 1.
+  const long long head = d < frames ? d : frames;
+  for (long long m = threadIdx.x; m < head; m += blockDim.x) {
+    const TIn r = x1[m];
+    acc.add(0.0, (double)r, 0.0f, (float)r);
   }
+  if (d < frames) {
+    const TIn* __restrict__ p0 = x0 + threadIdx.x;      // x0[m - d]
+    const TIn* __restrict__ p1 = x1 + d + threadIdx.x;  // x1[m]
+    const long long n = frames - d;
+    for (long long k = threadIdx.x; k < n; k += blockDim.x, p0 += blockDim.x, p1 += blockDim.x) {
+      const TIn l = *p0, r = *p1;
+      acc.add((double)l, (double)r, (float)l, (float)r);
+    }
+  }  // (d >= frames: the frames between the two channels are silence and add nothing to any sum)
+  const long long tail0 = frames > d ? frames : d;
+  for (long long m = tail0 + threadIdx.x; m < total; m += blockDim.x) {
+    const TIn l = x0[m - d];
+    acc.add((double)l, 0.0, (float)l, 0.0f);
+  }
+  double v[7] = {acc.v0, acc.v1, acc.v2, acc.v3, __longlong_as_double(acc.vmax), acc.v5, acc.v6};
   __shared__ double red[8][7];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
