@@ -8,7 +8,7 @@ mkdir -p "$out"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "$NVCC" -std=c++17 -O3 -lineinfo -fmad=false \
   -gencode arch=compute_100a,code=sm_100a \
-  -Xcompiler -fPIC,-O2 -shared \
+  -Xcompiler -fPIC,-O2 -shared -diag-suppress 177 \
   ${VND_PTXAS_V:+-Xptxas -v} \
   -o "$out/libvnd_b200.so" \
   ${VND_EXTRA_DEFS:-} \

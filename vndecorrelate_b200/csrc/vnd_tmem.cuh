@@ -164,7 +164,16 @@ __device__ __forceinline__ void near_issue(float (&t)[RG], uint32_t tcol) {
   if constexpr (RG == 16) {
     tmem_ld<16, 0>(t, tcol);
   } else if constexpr (RG == 32) {
+#if defined(VND_TM_PROBE) && VND_TM_PROBE == 1  // timing probe (results wrong by construction): half of the tensor-memory bytes per tap
+    tmem_ld<16, 0>(t, tcol);
+    tmem_ld<16, 16>(t, tcol);
+#elif defined(VND_TM_PROBE) && VND_TM_PROBE == 3  // ... a quarter
+    tmem_ld<16, 0>(t, tcol);
+#pragma unroll
+    for (int j = 16; j < 32; ++j) t[j] = 0.0f;
+#else
     tmem_ld<32, 0>(t, tcol);
+#endif
   } else if constexpr (RG == 48) {
     tmem_ld<32, 0>(t, tcol);
     tmem_ld<16, 32>(t, tcol + 32);
@@ -174,8 +183,13 @@ __device__ __forceinline__ void near_issue(float (&t)[RG], uint32_t tcol) {
 }
 template <bool SUB, int RG>
 __device__ __forceinline__ void near_add(const float (&t)[RG], float (&acc)[RG]) {
+#if defined(VND_TM_PROBE) && VND_TM_PROBE == 2  // timing probe (results wrong by construction): a quarter of the adds per tap
+  constexpr int kAdds = RG / 8;
+#else
+  constexpr int kAdds = RG / 2;
+#endif
 #pragma unroll
-  for (int j = 0; j < RG / 2; ++j) {
+  for (int j = 0; j < kAdds; ++j) {
     if constexpr (SUB) sub2(acc[2 * j], acc[2 * j + 1], t[2 * j], t[2 * j + 1]);
     else add2(acc[2 * j], acc[2 * j + 1], t[2 * j], t[2 * j + 1]);
   }
