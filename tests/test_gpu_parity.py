@@ -408,6 +408,81 @@ def test_planar_slab_tmem_kernel(api, frames, kappa, envelope, duration):
         raise AssertionError(f"{len(bad)} samples differ; first at (frame, channel) {bad[0]}, last {bad[-1]}")
 
 
+def test_randomised_decorrelate_against_the_oracle(api):
+    """120 seeded random (sample rate, duration, impulses, strength, envelope, mode, width, normaliser, filtered channels,
+    length, mono / stereo, dtype, seed) combinations of ``VelvetNoise.decorrelate`` (tests/_random_cases.py) on numpy input,
+    and on CUDA tensors for the float32 ones: dtype, shape and every bit must equal the oracle's, which
+    tests/test_oracle_golden.py pins to the reference's hashes of the same cases; where the reference raises (filters that
+    are not sparse), so must the library.  Lengths include 1, 2, 7 and 33 frames (shorter than any filter)."""
+    import json
+    import os
+
+    import torch
+
+    from tests import _random_cases as RC
+
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "random_decorrelate.json")))["cases"]
+    errors = {"ValueError": ValueError, "IndexError": IndexError, "TypeError": TypeError}
+    for (i, p, x), ref in zip(RC.cases(), golden):
+        kw = RC.vn_kwargs(p)
+        if "error" in ref:
+            with pytest.raises(errors[ref["error"]]):
+                api.VelvetNoise(**kw).decorrelate(x)
+            continue
+        vn = api.VelvetNoise(**kw)
+        want = RC.oracle_output(O, p, x)
+        got = vn.decorrelate(x)
+        assert got.dtype == want.dtype and got.shape == want.shape, (i, p, x.shape, x.dtype)
+        if not G.same_bits(np.ascontiguousarray(got), want):
+            bad = np.argwhere(np.ascontiguousarray(got).view(np.uint32) != want.view(np.uint32))
+            raise AssertionError(f"case {i} {p} input {x.shape} {x.dtype}: {len(bad)} samples differ, first {bad[0]}")
+        if x.dtype == np.float32:
+            got_t = vn.decorrelate(torch.from_numpy(x).cuda())
+            assert G.same_bits(np.ascontiguousarray(got_t.cpu().numpy()), want), (i, p, "tensor path")
+
+
+@pytest.mark.parametrize("family", ["convolve", "chain", "function"])
+def test_more_randomised_families_against_the_oracle(api, family):
+    """The three further families of tests/_random_cases.py (60 cases each): multichannel ``convolve`` on C- and
+    Fortran-order numpy arrays and on the matching CUDA tensors, ``SignalChain`` velvet noise + Haas, and
+    ``convolve_velvet_noise(generate_velvet_noise(...))``.  Bits, dtype and shape equal the oracle's (pinned to the
+    reference's hashes on the CPU side); the reference's exceptions are raised where it raises."""
+    import json
+    import os
+
+    import torch
+
+    from tests import _random_cases as RC
+
+    rows = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "random_decorrelate.json")))["more"][family]
+    errors = {"ValueError": ValueError, "IndexError": IndexError, "TypeError": TypeError}
+    oracle = {"convolve": RC.oracle_convolve, "chain": RC.oracle_chain, "function": RC.oracle_function}[family]
+
+    def run(p, x):
+        if family == "convolve":
+            return api.VelvetNoise(**RC.convolve_kwargs(p)).convolve(x)
+        if family == "chain":
+            return RC.run_chain(api.SignalChain, p, x)
+        return api.convolve_velvet_noise(x, api.generate_velvet_noise(**RC.function_kwargs(p)))
+
+    for (i, p, x), ref in zip(RC.more_cases(family), rows):
+        if "error" in ref:
+            with pytest.raises(errors[ref["error"]]):
+                run(p, x)
+            continue
+        want = oracle(O, p, x)
+        got = run(p, x)
+        assert got.dtype == want.dtype and got.shape == want.shape, (family, i, p, x.shape, x.dtype)
+        if not G.same_bits(np.ascontiguousarray(got), want):
+            bad = np.argwhere(np.ascontiguousarray(got).view(np.uint8) != want.view(np.uint8))
+            raise AssertionError(f"{family} case {i} {p} input {x.shape} {x.dtype}: bytes differ, first at {bad[0]}")
+        if family == "convolve" and x.dtype == np.float32:  # the same view of the data as a CUDA tensor
+            xt = torch.from_numpy(np.ascontiguousarray(x.T)).cuda().t() if x.flags.f_contiguous and not x.flags.c_contiguous \
+                else torch.from_numpy(np.ascontiguousarray(x)).cuda()
+            got_t = run(p, xt)
+            assert G.same_bits(np.ascontiguousarray(got_t.cpu().numpy()), want), (family, i, p, "tensor path")
+
+
 @pytest.mark.parametrize("shape", list(range(1, 13)))
 def test_tmem_kernel_variants_are_bit_exact(api, shape):
     """Every measured variant of the tensor-memory kernel (shapes, software pipelining, paired first / far segments,

@@ -293,3 +293,53 @@ def test_oracle_random_tap_tables_match_reference():
                           sample_rate_hz=p["sample_rate_hz"], segment_envelope=tuple(p["segment_envelope"]),
                           log_distribution_strength=p["log_distribution_strength"], seed=p["seed"])
         assert G.sha(fir) == rec["dense_sha256"], p
+
+
+def test_oracle_matches_reference_on_random_decorrelate_cases():
+    """The 120 seeded random ``VelvetNoise.decorrelate`` cases of tests/_random_cases.py: the oracle's output hashes (dtype,
+    shape, sha256 of the bytes) equal the ones tests/golden/make_golden_r02b.py took from the unmodified reference; the
+    cases the reference rejects are listed with its exception type and are checked against the library on the GPU."""
+    import hashlib
+    import json
+    import os
+
+    from tests import _random_cases as RC
+
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "random_decorrelate.json")))
+    assert golden["seed"] == RC.SEED and golden["count"] == RC.COUNT == len(golden["cases"])
+    checked = 0
+    for (i, p, x), ref in zip(RC.cases(), golden["cases"]):
+        assert ref["id"] == i
+        if "error" in ref:
+            continue
+        y = np.ascontiguousarray(RC.oracle_output(O, p, x))
+        assert str(y.dtype) == ref["dtype"] and list(y.shape) == ref["shape"], (i, p)
+        assert hashlib.sha256(y.tobytes()).hexdigest() == ref["sha256"], (i, p)
+        checked += 1
+    assert checked >= 100
+
+
+@pytest.mark.parametrize("family", ["convolve", "chain", "function"])
+def test_oracle_matches_reference_on_more_random_families(family):
+    """60 seeded random cases each of multichannel ``convolve`` (C and Fortran order, float32 / float64, an unused input
+    channel), ``SignalChain`` velvet noise + Haas (all modes, widths, mono, int16) and the function path
+    ``convolve_velvet_noise(generate_velvet_noise(...))``: the oracle reproduces the reference's hashes."""
+    import hashlib
+    import json
+    import os
+
+    from tests import _random_cases as RC
+
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "random_decorrelate.json")))
+    fn = {"convolve": RC.oracle_convolve, "chain": RC.oracle_chain, "function": RC.oracle_function}[family]
+    rows = golden["more"][family]
+    assert golden["count_more"] == RC.COUNT_MORE == len(rows)
+    checked = 0
+    for (i, p, x), ref in zip(RC.more_cases(family), rows):
+        if "error" in ref:
+            continue
+        y = np.ascontiguousarray(fn(O, p, x))
+        assert str(y.dtype) == ref["dtype"] and list(y.shape) == ref["shape"], (i, p)
+        assert hashlib.sha256(y.tobytes()).hexdigest() == ref["sha256"], (i, p)
+        checked += 1
+    assert checked >= 55
