@@ -91,8 +91,9 @@ constexpr int kBarBytes = 384;
 //                        (pair_first in vnd_tmem.cuh); TMEM is handed over in two column stages
 //   <3, 32, 3, 144, 80, false, false, false, true>  round 2: the lane quarters take their shared-memory phase in two
 //                        alternating groups (kGate, see compute_main)
-template <int G, int RG, int NBUF, int RC, int RH, bool PIPE = false, bool PAIR = false, bool PARK = false, int GATE = 0, int FF = 0>
+template <int G, int RG, int NBUF, int RC, int RH, bool PIPE = false, bool PAIR = false, bool PARK = false, int GATE = 0, int FF = 0, bool DUAL = false>
 struct TmShape {
+  static constexpr bool kDual = DUAL;          // two tensor-memory taps per round trip (two landing buffers, one wait)
   static constexpr bool kFarFirst = FF != 0;   // the trailing all-far segment first (sum parked in the staging row), under the TMEM refill:
   static constexpr int kFarFirstMode = FF;     // 1: every warp, double-buffered loads; 2: only the last warp of each quarter (two warps
                                                // per scheduler in the tensor-memory taps at a time), 3: every warp, plain loop
@@ -552,7 +553,7 @@ __device__ __noinline__ void compute_main(const TmParams& P, uint32_t tbase, int
         }
       }
       if (!(T::kPair || T::kFarFirst) || !pair_ok) {
-        run_segments<false, T::kPipe>(segtab, 0, near_end, ops, tcol0, row, yv);
+        run_segments<false, T::kPipe, RG, T::kDual>(segtab, 0, near_end, ops, tcol0, row, yv);
         VND_TRACE(ti, 2);
         tmem_fence_before();
         __syncwarp();
@@ -632,7 +633,7 @@ static const int g_stagger_ns = [] {
   return e ? atoi(e) : 2000;
 }();
 // VND_TM_SHAPE picks the kernel variant (see TmShape and fir_tmem_launch): 0 = 3 x 32 (default), 1 = 2 x 48, 2 = 2 x 64, 3 = 2 x 32,
-// 4 = 3 pipelined, 5-12 = scheduling variants of the default shape.
+// 4 = 3 pipelined, 5-14 = scheduling variants of the default shape.
 static int g_tm_shape = [] {
   const char* e = getenv("VND_TM_SHAPE");
   return e ? atoi(e) : VND_TM_DEFAULT_SHAPE;
@@ -758,6 +759,8 @@ static int fir_tmem_launch_t(const FirParams& f, int max_prog_words, cudaStream_
 //   9 / 10: 8 with kGate 2 / 4                                                                                      306 / 219
 //   11: all-far segment first on the last warp of each quarter only (two warps per scheduler in TMEM taps)        307
 //   12: all-far segment first on every warp, plain loop                                                            344
+//   13 / 14: two tensor-memory taps per round trip (both loads issued, one wait, then both sets of adds; kDual),   300 / 278
+//      152 / 56 and 144 / 80 registers (16 / 128 bytes of spilled scalars)
 // The per-warp chain of a tap (~240 clk from tensor memory, ~400 clk from shared memory) does not shorten when fewer
 // warps contend (far phase 3.2 k clk per tile with one quarter in it, 3.5 k with two, 3.8 k with four), so taking turns
 // buys nothing, and every form of overlap inside a warp has made the taps slower.
@@ -775,6 +778,8 @@ int fir_tmem_launch(const FirParams& f, int max_prog_words, cudaStream_t st, lon
     case 10: return fir_tmem_launch_t<TmShape<3, 32, 3, 144, 80, false, false, false, 4, 1>>(f, max_prog_words, st, frames_done);
     case 11: return fir_tmem_launch_t<TmShape<3, 32, 3, 144, 80, false, false, false, 0, 2>>(f, max_prog_words, st, frames_done);
     case 12: return fir_tmem_launch_t<TmShape<3, 32, 3, 144, 80, false, false, false, 0, 3>>(f, max_prog_words, st, frames_done);
+    case 13: return fir_tmem_launch_t<TmShape<3, 32, 3, 152, 56, false, false, false, 0, 0, true>>(f, max_prog_words, st, frames_done);
+    case 14: return fir_tmem_launch_t<TmShape<3, 32, 3, 144, 80, false, false, false, 0, 0, true>>(f, max_prog_words, st, frames_done);
     default: return fir_tmem_launch_t<TmShape<3, 32, 3, 144, 80>>(f, max_prog_words, st, frames_done);
   }
 }

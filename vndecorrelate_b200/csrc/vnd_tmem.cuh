@@ -323,7 +323,7 @@ __device__ __forceinline__ void one_tap(int op, uint32_t tcol0, uint32_t row, fl
 // The loops are unrolled by two with the operation words in alternating registers, so that each word
 // is loaded a whole tap before it is needed and never copied (a single loop-carried register made
 // ptxas copy the loaded word at once and stall on the shared-memory latency at every tap).
-template <bool SUB, bool ALLFAR, bool PIPE, int RG>
+template <bool SUB, bool ALLFAR, bool PIPE, int RG, bool DUAL = false>
 __device__ __forceinline__ void tap_list(const int* __restrict__ ops, int n, int nn, uint32_t tcol0, uint32_t row, float (&acc)[RG]) {
   if (n <= 0) return;
   int k = 0;
@@ -357,6 +357,29 @@ __device__ __forceinline__ void tap_list(const int* __restrict__ ops, int n, int
       if (k >= n) return;
       op_a = ops[k];
     }
+  } else if constexpr (!ALLFAR && DUAL) {
+    // Two taps per tensor-memory round trip: both loads are issued, ONE wait covers them (tcgen05.wait::ld waits for every
+    // outstanding load of the thread anyway), then both sets of adds.  Needs a second landing buffer (64 registers).
+    for (; k + 1 < nn; k += 2) {
+      const int op_b = ops[k + 1];
+      float ta[RG], tb[RG];
+      near_issue(ta, tcol0 + (uint32_t)op_a);
+      near_issue(tb, tcol0 + (uint32_t)op_b);
+      op_a = ops[k + 2];  // two words of slack follow the lists
+      tmem_wait_ld(ta);
+      tmem_wait_ld(tb);
+      near_add<SUB>(ta, acc);
+      near_add<SUB>(tb, acc);
+    }
+    if (k < nn) {
+      float t[RG];
+      near_issue(t, tcol0 + (uint32_t)op_a);
+      tmem_wait_ld(t);
+      near_add<SUB>(t, acc);
+      ++k;
+      op_a = ops[k];
+    }
+    if (k >= n) return;
   } else if constexpr (!ALLFAR) {
     for (; k < nn; k += 2) {  // near prefix
       const int op_b = ops[k + 1];  // two words of slack follow the lists, so the prefetches stay in bounds
@@ -394,7 +417,7 @@ __device__ __forceinline__ void tap_list(const int* __restrict__ ops, int n, int
 // Segments [s0, s1) of the program added into the running output, in the reference's order
 // (decorrelation.py:402-414): acc = 0; acc -= x[n + i] over the negative list; acc += x[n + i] over
 // the positive list; acc *= gain; y += acc.
-template <bool ALLFAR, bool PIPE, int RG>
+template <bool ALLFAR, bool PIPE, int RG, bool DUAL = false>
 __device__ __forceinline__ void run_segments(const int4* __restrict__ segtab, int s0, int s1, const int*& ops, uint32_t tcol0, uint32_t row,
                                              float (&yv)[RG]) {
   for (int s = s0; s < s1; ++s) {
@@ -404,8 +427,8 @@ __device__ __forceinline__ void run_segments(const int4* __restrict__ segtab, in
 #pragma unroll
     for (int r = 0; r < RG; ++r) acc[r] = 0.0f;
     const int nn = ALLFAR ? 0 : d.z;  // leading tensor-memory taps: neg list in the low half, pos list in the high half
-    tap_list<true, ALLFAR, PIPE>(ops, n_neg, nn & 0xffff, tcol0, row, acc);
-    tap_list<false, ALLFAR, PIPE>(ops + n_neg, n_pos, nn >> 16, tcol0, row, acc);
+    tap_list<true, ALLFAR, PIPE, RG, DUAL>(ops, n_neg, nn & 0xffff, tcol0, row, acc);
+    tap_list<false, ALLFAR, PIPE, RG, DUAL>(ops + n_neg, n_pos, nn >> 16, tcol0, row, acc);
     ops += n_neg + n_pos;
     {  // 1.0f when the program carries no gains (x * 1 == x bit for bit)
       const float gain = __int_as_float(d.w);
