@@ -518,6 +518,26 @@ def test_tmem_kernel_variants_are_bit_exact(api, shape):
         lib.vnd_debug_set_tm_shape(prev)
 
 
+def test_many_channels_every_sample(api):
+    """600 channels x 65 000 frames (more runs than four waves of persistent CTAs, one tap table sliced over all of them):
+    EVERY output sample of every channel against the oracle, not just windows of the first and the last channel as in
+    bench.py's spot check."""
+    import torch
+
+    Cn, frames = 600, 65000
+    vn = api.VelvetNoise(sample_rate_hz=48000, duration_seconds=0.03, num_impulses=30, num_outs=Cn, filtered_channels=tuple(range(Cn)), mode="LR",
+                         normalizer=None, seed=3)
+    g = torch.Generator(device="cuda").manual_seed(123)
+    slab = torch.randn((Cn, frames), generator=g, device="cuda") * 0.1
+    y = vn.convolve(slab.t())
+    taps = O.class_taps(sample_rate_hz=48000, duration_seconds=0.03, num_impulses=30, num_outs=Cn, filtered_channels=tuple(range(Cn)), seed=3)
+    want = O.fir_class_order(np.ascontiguousarray(slab.cpu().numpy().T), taps, O.DEFAULT_ENVELOPE, Cn)
+    got = np.ascontiguousarray(y.cpu().numpy())
+    if not G.same_bits(got, want):
+        bad = np.argwhere(got.view(np.uint32) != want.view(np.uint32))
+        raise AssertionError(f"{len(bad)} samples differ; first at (frame, channel) {bad[0]}, channels {np.unique(bad[:, 1])[:10]}")
+
+
 def test_planar_slab_unaligned_falls_back(api):
     """A channel stride that is not a multiple of 4 samples cannot use the bulk copy."""
     import torch
