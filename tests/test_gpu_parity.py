@@ -483,7 +483,7 @@ def test_more_randomised_families_against_the_oracle(api, family):
             assert G.same_bits(np.ascontiguousarray(got_t.cpu().numpy()), want), (family, i, p, "tensor path")
 
 
-@pytest.mark.parametrize("shape", list(range(1, 15)))
+@pytest.mark.parametrize("shape", list(range(1, 16)))
 def test_tmem_kernel_variants_are_bit_exact(api, shape):
     """Every measured variant of the tensor-memory kernel (shapes, software pipelining, paired first / far segments,
     alternating far phases, far-first, two taps per round trip; vnd_fir_tmem.cu: fir_tmem_launch) must produce the default kernel's - the oracle's -

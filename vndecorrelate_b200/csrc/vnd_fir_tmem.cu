@@ -91,8 +91,10 @@ constexpr int kBarBytes = 384;
 //                        (pair_first in vnd_tmem.cuh); TMEM is handed over in two column stages
 //   <3, 32, 3, 144, 80, false, false, false, true>  round 2: the lane quarters take their shared-memory phase in two
 //                        alternating groups (kGate, see compute_main)
-template <int G, int RG, int NBUF, int RC, int RH, bool PIPE = false, bool PAIR = false, bool PARK = false, int GATE = 0, int FF = 0, bool DUAL = false>
+template <int G, int RG, int NBUF, int RC, int RH, bool PIPE = false, bool PAIR = false, bool PARK = false, int GATE = 0, int FF = 0, bool DUAL = false, bool SYM = false>
 struct TmShape {
+  static constexpr bool kSym = SYM;            // no data-movement warps: every warp computes, refills its share of the TMEM rows, and
+                                               // elected lanes issue the tile loads and the stores (sym_main)
   static constexpr bool kDual = DUAL;          // two tensor-memory taps per round trip (two landing buffers, one wait)
   static constexpr bool kFarFirst = FF != 0;   // the trailing all-far segment first (sum parked in the staging row), under the TMEM refill:
   static constexpr int kFarFirstMode = FF;     // 1: every warp, double-buffered loads; 2: only the last warp of each quarter (two warps
@@ -106,7 +108,8 @@ struct TmShape {
   static constexpr int kRG = RG;               // outputs per thread
   static constexpr int kR = G * RG;            // outputs per row
   static constexpr int kCW = 4 * G;            // compute warps (warp w: lane quarter w & 3, group w >> 2)
-  static constexpr int kNW = kCW + 4;          // plus one data-movement warp per quarter
+  static constexpr int kHelpers = SYM ? 0 : 4; // one data-movement warp per quarter
+  static constexpr int kNW = kCW + kHelpers;
   static constexpr int kNT = kNW * 32;
   static constexpr int kTile = kRows * kR;
   static constexpr int kPitch = kR + 4;        // row pitch in shared memory (words); an odd number of 16-byte chunks
@@ -119,7 +122,8 @@ struct TmShape {
                        B_TM_FREE = 2 * NBUF + 12, B_TM_FULL2 = 2 * NBUF + 16, B_FAR_DONE = 2 * NBUF + 20, B_COUNT = 2 * NBUF + 24;
   static_assert(RG == 32 || RG == 48 || RG == 64, "outputs per thread: one x32, x32 + x16 or x64 tcgen05.ld");
   static_assert(kR % 32 == 0 && ((kPitch / 4) & 1) == 1, "rows are whole 32-column units; the pitch is an odd number of chunks");
-  static_assert(32 * (kCW * RC + 4 * RH) <= kLaunchRegs * kNT, "register file");
+  static_assert(32 * (kCW * RC + kHelpers * RH) <= kLaunchRegs * kNT, "register file");
+  static_assert(!SYM || (kUnits % G == 0 && !PIPE && !PAIR && GATE == 0 && FF == 0 && !DUAL), "symmetric variant: plain loops, equal fill shares");
   static_assert(RC % 8 == 0 && RH % 8 == 0, "setmaxnreg takes multiples of 8");
   static_assert(B_COUNT * 8 <= 256, "mbarriers");
   static_assert(GATE == 0 || GATE == 2 || GATE == 4, "far-phase gate");
@@ -586,6 +590,127 @@ __device__ __noinline__ void compute_main(const TmParams& P, uint32_t tbase, int
   }
 }
 
+// ---------------------------------------------------------------- symmetric variant: warp (q, g) does everything
+// No data-movement warps (TmShape::kSym): G = 4 warps per quarter x 32 outputs, rows of 128, 16 x 128 registers.  Each
+// warp fills its share of the quarter's TMEM rows (group g: the 128 columns that are row m + g's samples) at the top of
+// a tile, then runs the tile like compute_main; lane 0 of warp 0 issues the tile loads (two buffers), lane 0 of the
+// first warp of each quarter the quarter's output store.
+template <class T>
+__device__ __noinline__ void sym_main(const TmParams& P, uint32_t tbase, int tid) {
+  constexpr int RG = T::kRG;
+  constexpr int kShare = kUnits / T::kG;  // 32-column units of a row that one warp fills
+  static_assert(kShare * 32 == T::kR, "a warp's fill share is one block of the row");
+  const Smem<T> sm(P);
+  const int nblk = P.nblk, n_runs = P.n_runs;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int q = warp & 3, g = warp >> 2;
+  const int m = 32 * q + lane;
+  uint64_t* bars = sm.bars;
+  const uint32_t bars32 = smem_u32(sm.bars), in0 = smem_u32(sm.in_all), buf_bytes = (uint32_t)sm.bufw * 4u;
+  const uint32_t stage_q = smem_u32(sm.stage + 32 * q * T::kPitch);
+  const uint32_t tx_bytes = (uint32_t)nblk * (T::kPitch * 4u);
+  const void* tmx = &P.tmx;
+  const void* tmy = &P.tmy;
+  const bool loader = tid == 0, storer = g == 0 && lane == 0;
+  const uint32_t tcol0 = tbase + (uint32_t)(RG * g);
+  const int4* segtab = sm.segtab;
+  int b = 0, lb = 0;            // ring slots of the current tile and of the next load
+  unsigned fpar = 0, lpar = 1;  // in_full parity of slot b; in_free parity that releases slot lb
+  unsigned tpar = 0;            // parity of the tile counter
+  for (int run = blockIdx.x; run < n_runs; run += gridDim.x) {
+    RunInfo r;
+    if (!begin_run<T>(P, sm, run, tid, r)) continue;
+    const int S = sm.sprog[0];
+    const int near_end = *sm.s_near_end;
+    int load_row = r.first_tile * kRows, to_load = r.n_tiles;
+    int store_row = r.first_tile * kRows + 32 * q;
+    auto issue_load = [&]() {  // loader lane only
+      mbar_wait_u32(bars32 + 8u * (T::B_IN_FREE + lb), lpar);  // every warp is done with the tile that was there
+      const uint32_t full = bars32 + 8u * (T::B_IN_FULL + lb);
+      mbar_expect_tx_u32(full, tx_bytes);
+      fence_proxy_async();
+      tma_load_3d(in0 + (uint32_t)lb * buf_bytes, tmx, 0, load_row, r.c, full);
+      load_row += kRows;
+      --to_load;
+      if (++lb == T::kNBuf) {
+        lb = 0;
+        lpar ^= 1u;
+      }
+    };
+    if (loader)
+      for (int d = 0; d < T::kNBuf && to_load > 0; ++d) issue_load();
+    __syncwarp();
+    for (int ti = 0; ti < r.n_tiles; ++ti) {
+      const uint32_t row = smem_u32(sm.in_all + b * sm.bufw + m * T::kPitch);
+      const int* ops = sm.ops + g * sm.opstride;
+      VND_TRACE(ti, 0);
+      mbar_wait(&bars[T::B_IN_FULL + b], fpar);
+      mbar_wait(&bars[T::B_TM_FREE + q], tpar ^ 1u);  // every warp of the quarter is past its last TMEM tap of the previous tile
+      tmem_fence_after();
+      {  // this warp's share of the rows: row m + g's samples are columns [R g, R g + R) of TMEM row m
+        const float4* src = reinterpret_cast<const float4*>(sm.in_all + b * sm.bufw + (m + g) * T::kPitch);
+        uint32_t tcol = tbase + (uint32_t)(T::kR * g);
+#pragma unroll 1
+        for (int u = 0; u < kShare; ++u) {
+          float4 v[8];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) v[jj] = src[jj];
+          tmem_st32(tcol, v);
+          tcol += 32;
+          src += 8;
+        }
+        tmem_wait_st();
+      }
+      tmem_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[T::B_TM_FULL + q]);
+      VND_TRACE(ti, 6);
+      float yv[RG];
+#pragma unroll
+      for (int rr = 0; rr < RG; ++rr) yv[rr] = 0.0f;
+      mbar_wait(&bars[T::B_TM_FULL + q], tpar);
+      tmem_fence_after();
+      VND_TRACE(ti, 1);
+      run_segments<false, false>(segtab, 0, near_end, ops, tcol0, row, yv);
+      VND_TRACE(ti, 2);
+      tmem_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[T::B_TM_FREE + q]);
+      run_segments<true, false>(segtab, near_end, S, ops, tcol0, row, yv);
+      VND_TRACE(ti, 3);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[T::B_IN_FREE + b]);  // this warp is done with the tile buffer
+      mbar_wait(&bars[T::B_ST_FREE + q], tpar ^ 1u);       // the previous tile's store has read the staging rows
+      VND_TRACE(ti, 5);
+      {
+        float4* dst = reinterpret_cast<float4*>(sm.stage + m * T::kPitch + RG * g);
+#pragma unroll
+        for (int jj = 0; jj < RG / 4; ++jj) dst[jj] = make_float4(yv[4 * jj], yv[4 * jj + 1], yv[4 * jj + 2], yv[4 * jj + 3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[T::B_ST_FULL + q]);
+      VND_TRACE(ti, 4);
+      if (storer) {  // the quarter's 32 staged rows, once its G warps have staged them
+        mbar_wait_u32(bars32 + 8u * (T::B_ST_FULL + q), tpar);
+        tma_store_3d(tmy, 0, store_row, r.c, stage_q);
+        bulk_commit();
+        bulk_wait_read0();
+        mbar_arrive_u32(bars32 + 8u * (T::B_ST_FREE + q));
+      }
+      store_row += kRows;
+      if (loader && to_load > 0) issue_load();
+      __syncwarp();
+      VND_TRACE(ti, 7);
+      tpar ^= 1u;
+      if (++b == T::kNBuf) {
+        b = 0;
+        fpar ^= 1u;
+      }
+    }
+  }
+}
+
 template <class T>
 __global__ void __launch_bounds__(T::kNT, 1) fir_tmem_kernel(const __grid_constant__ TmParams P) {
   const Smem<T> sm(P);
@@ -596,12 +721,12 @@ __global__ void __launch_bounds__(T::kNT, 1) fir_tmem_kernel(const __grid_consta
   if (tid == 0) {
     for (int b = 0; b < T::kNBuf; ++b) {
       mbar_init(&sm.bars[T::B_IN_FULL + b], 1);
-      mbar_init(&sm.bars[T::B_IN_FREE + b], T::kCW + 4);
+      mbar_init(&sm.bars[T::B_IN_FREE + b], T::kCW + T::kHelpers);
     }
     for (int k = 0; k < 4; ++k) {
       mbar_init(&sm.bars[T::B_ST_FULL + k], T::kG);
       mbar_init(&sm.bars[T::B_ST_FREE + k], 1);
-      mbar_init(&sm.bars[T::B_TM_FULL + k], 1);
+      mbar_init(&sm.bars[T::B_TM_FULL + k], T::kSym ? T::kG : 1);
       mbar_init(&sm.bars[T::B_TM_FREE + k], T::kG);
       mbar_init(&sm.bars[T::B_TM_FULL2 + k], 1);
     }
@@ -613,7 +738,9 @@ __global__ void __launch_bounds__(T::kNT, 1) fir_tmem_kernel(const __grid_consta
   __syncthreads();
   tmem_fence_after();
   const uint32_t tbase = *tm_slot + ((uint32_t)(32 * (warp & 3)) << 16);
-  if (warp >= T::kCW) {
+  if constexpr (T::kSym) {
+    sym_main<T>(P, tbase, tid);
+  } else if (warp >= T::kCW) {
     set_max_regs_dec<T::kRegsHelper>();
     helper_main<T>(P, tbase, tid);
   } else {
@@ -633,7 +760,7 @@ static const int g_stagger_ns = [] {
   return e ? atoi(e) : 2000;
 }();
 // VND_TM_SHAPE picks the kernel variant (see TmShape and fir_tmem_launch): 0 = 3 x 32 (default), 1 = 2 x 48, 2 = 2 x 64, 3 = 2 x 32,
-// 4 = 3 pipelined, 5-14 = scheduling variants of the default shape.
+// 4 = 3 pipelined, 5-14 = scheduling variants of the default shape, 15 = symmetric 4 x 32.
 static int g_tm_shape = [] {
   const char* e = getenv("VND_TM_SHAPE");
   return e ? atoi(e) : VND_TM_DEFAULT_SHAPE;
@@ -759,8 +886,12 @@ static int fir_tmem_launch_t(const FirParams& f, int max_prog_words, cudaStream_
 //   9 / 10: 8 with kGate 2 / 4                                                                                      306 / 219
 //   11: all-far segment first on the last warp of each quarter only (two warps per scheduler in TMEM taps)        307
 //   12: all-far segment first on every warp, plain loop                                                            344
+//   15: symmetric CTA, 4 warps per quarter x 32 outputs, rows of 128, no data-movement warps (sym_main)          355
 //   13 / 14: two tensor-memory taps per round trip (both loads issued, one wait, then both sets of adds; kDual),   300 / 278
 //      152 / 56 and 144 / 80 registers (16 / 128 bytes of spilled scalars)
+// With four warps per scheduler (15) a tensor-memory tap takes 300 clk per warp, with three 240, with two of the three (11)
+// still 240 while the third is elsewhere: ~75-80 clk of the quarter's TMEM read path per x32 load however many warps ask,
+// i.e. ~54 B/clk per scheduler - the tensor-memory phase (22 taps x 3 warps x 4 KB) is bound by that path.
 // The per-warp chain of a tap (~240 clk from tensor memory, ~400 clk from shared memory) does not shorten when fewer
 // warps contend (far phase 3.2 k clk per tile with one quarter in it, 3.5 k with two, 3.8 k with four), so taking turns
 // buys nothing, and every form of overlap inside a warp has made the taps slower.
@@ -780,6 +911,7 @@ int fir_tmem_launch(const FirParams& f, int max_prog_words, cudaStream_t st, lon
     case 12: return fir_tmem_launch_t<TmShape<3, 32, 3, 144, 80, false, false, false, 0, 3>>(f, max_prog_words, st, frames_done);
     case 13: return fir_tmem_launch_t<TmShape<3, 32, 3, 152, 56, false, false, false, 0, 0, true>>(f, max_prog_words, st, frames_done);
     case 14: return fir_tmem_launch_t<TmShape<3, 32, 3, 144, 80, false, false, false, 0, 0, true>>(f, max_prog_words, st, frames_done);
+    case 15: return fir_tmem_launch_t<TmShape<4, 32, 2, 128, 0, false, false, false, 0, 0, false, true>>(f, max_prog_words, st, frames_done);
     default: return fir_tmem_launch_t<TmShape<3, 32, 3, 144, 80>>(f, max_prog_words, st, frames_done);
   }
 }

@@ -382,7 +382,12 @@ __device__ __forceinline__ void tap_list(const int* __restrict__ ops, int n, int
     if (k >= n) return;
   } else if constexpr (!ALLFAR) {
     for (; k < nn; k += 2) {  // near prefix
+#if defined(VND_TM_PROBE) && VND_TM_PROBE == 4  // timing probe (results wrong by construction): tap columns without the operation words
+      const int op_b = 8 * k + 8;
+      op_a = 8 * k;
+#else
       const int op_b = ops[k + 1];  // two words of slack follow the lists, so the prefetches stay in bounds
+#endif
       {
         float t[RG];
         near_issue(t, tcol0 + (uint32_t)op_a);
