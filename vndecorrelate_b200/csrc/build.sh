@@ -6,7 +6,7 @@ here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 out="$here/../_lib"
 mkdir -p "$out"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-"$NVCC" -std=c++17 -O3 -lineinfo -fmad=false \
+"$NVCC" -std=c++17 -O3 -lineinfo -fmad=false --threads 0 \
   -gencode arch=compute_100a,code=sm_100a \
   -Xcompiler -fPIC,-O2 -shared -diag-suppress 177 \
   ${VND_PTXAS_V:+-Xptxas -v} \
