@@ -214,7 +214,11 @@ __device__ __forceinline__ void far_tap_a(uint32_t row, int op, float (&acc)[RG]
   const uint32_t p = row + 4u * (uint32_t)(op & 0xffff);  // `row`: shared-memory address of the thread's row
   const int kx = (op >> 16) & 31;
   float4 c[NC];
+#if defined(VND_TM_PROBE) && (VND_TM_PROBE == 5 || VND_TM_PROBE == 7)  // timing probe (results wrong by construction): no block crossing
+  if (true) {
+#else
   if (kx >= NC) {
+#endif
 #pragma unroll
     for (int k = 0; k < NC; ++k) c[k] = lds128(p + 16u * k);
   } else {
@@ -295,6 +299,10 @@ constexpr int kOpFar = (int)0x80000000u;
 
 template <bool SUB, int RG>
 __device__ __forceinline__ void far_tap(uint32_t row, int op, float (&acc)[RG]) {
+#if defined(VND_TM_PROBE) && (VND_TM_PROBE == 6 || VND_TM_PROBE == 7)  // timing probe (results wrong by construction): every far tap as an aligned one
+  far_tap_a<0, SUB>(row, op, acc);
+  return;
+#endif
   switch ((op >> 24) & 3) {
     case 0: far_tap_a<0, SUB>(row, op, acc); break;
     case 1: far_tap_a<1, SUB>(row, op, acc); break;
