@@ -538,8 +538,10 @@ def run_cfg3(env: Env, args, lib, N, R, VelvetNoise, C):
                 "kernel": "fir_tmem_kernel (tensor-memory Hankel rows + tcgen05.ld gathers, FADD2, warp-specialised, tensor-map TMA); the last "
                           "~1.5 tiles of every channel run on fir_window_kernel in a second launch inside the same step",
                 "kernel_ms": kernel_ms, "peak_source": peak_src,
-                "note": "HBM is not the binding resource: every (output, tap) pair moves one word from on-chip memory to a register; the kernel "
-                        "is bound by the shared-memory pipe and on-chip latency. See DESIGN.md section 4 and profiles/"}
+                "note": "HBM is not the binding resource: every (output, tap) pair moves one word from on-chip memory to a register. Per lane "
+                        "quarter a tile is the sum of the tensor-memory phase (22 taps; bound by the quarter's TMEM read path, ~54 B/clk per "
+                        "scheduler) and the shared-memory phase (8 far taps: a per-warp instruction chain), which cannot overlap because the "
+                        "quarter's TMEM rows are refilled as a whole. See DESIGN.md section 4 and profiles/r02_summary.md"}
 
     # end to end through the PYTHON API with host buffers: VelvetNoise.convolve on a page-locked C-order (frames, channels)
     # numpy slab (the reference's layout), numpy result; upload / transposes / kernel / download overlapped inside the call
