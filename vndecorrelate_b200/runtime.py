@@ -138,9 +138,12 @@ class _PinnedBlock:
     def __init__(self, ptr: int, nbytes: int):
         self.ptr, self.nbytes, self.pid = ptr, nbytes, os.getpid()
 
-    def __del__(self):
-        if self.pid == os.getpid():  # a forked child must not recycle pointers registered in its parent's CUDA context
-            _pinned_pool_release(self.ptr, self.nbytes)
+    def __del__(self, _getpid=os.getpid):  # bound at definition: module globals may already be gone at interpreter shutdown
+        try:
+            if self.pid == _getpid():  # a forked child must not recycle pointers registered in its parent's CUDA context
+                _pinned_pool_release(self.ptr, self.nbytes)
+        except Exception:  # interpreter shutdown: the pool and the library are being torn down anyway
+            pass
 
 
 _POOL_LOCK = threading.RLock()  # re-entrant: a garbage collection inside the locked region may release another block
