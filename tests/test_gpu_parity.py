@@ -581,6 +581,38 @@ def test_cfg4_long_filter_large_halo(api):
     assert G.same_bits(np.ascontiguousarray(y.cpu().numpy()), want)
 
 
+@pytest.mark.parametrize(
+    "fs,duration,n_imp,envelope,frames,filtered",
+    [
+        (96000, 0.3, 300, (0.85, 0.55, 0.35, 0.2), 700003, (0, 1, 2)),      # BASELINE config 4's filter, several runs per channel, channel 3 copied
+        (96000, 0.2, 120, (1.0,), 400000, (0, 1, 2, 3)),                    # identity envelope (no gain multiply), four ring slots less one
+        (48000, 0.25, 64, (0.9, -0.5, 0.25), 262144 + 8192 * 4, (0, 1)),    # frames a whole number of steps: no tail at all behind the ring's share
+        (96000, 0.3, 300, (0.85, 0.55, 0.35, 0.2), 8192 * 12 + 5, (0, 1, 2, 3)),  # the shortest slab the ring kernel takes (eight steps)
+    ],
+)
+def test_ring_kernel_long_filters(api, fs, duration, n_imp, envelope, frames, filtered):
+    """Long filters on long planar slabs: the interior of every channel goes through the ring-buffer kernel
+    (vnd_fir_ring.cu: persistent CTAs, every sample fetched once), the tail through the tile kernels; every output sample
+    must equal the oracle's."""
+    import torch
+
+    Cn = 4
+    vn = api.VelvetNoise(sample_rate_hz=fs, duration_seconds=duration, num_impulses=n_imp, num_outs=Cn, filtered_channels=filtered, mode="LR",
+                         normalizer=None, segment_envelope=envelope, seed=9)
+    g = torch.Generator(device="cuda").manual_seed(31)
+    slab = torch.randn((Cn, frames), generator=g, device="cuda") * 0.1
+    slab[0, 1000:9000] = 0.0
+    slab[0, 9000:9100] = -0.0
+    y = vn.convolve(slab.t())
+    taps = O.class_taps(sample_rate_hz=fs, duration_seconds=duration, num_impulses=n_imp, num_outs=Cn, num_segments=len(envelope),
+                        filtered_channels=filtered, seed=9)
+    want = O.fir_class_order(np.ascontiguousarray(slab.cpu().numpy().T), taps, envelope, Cn)
+    got = np.ascontiguousarray(y.cpu().numpy())
+    if not G.same_bits(got, want):
+        bad = np.argwhere(got.view(np.uint32) != want.view(np.uint32))
+        raise AssertionError(f"{len(bad)} samples differ; first at (frame, channel) {bad[0]}, last {bad[-1]}")
+
+
 def test_filter_longer_than_shared_memory_uses_direct_kernel(api):
     rng = np.random.default_rng(4)
     x = (rng.standard_normal((300000, 2)) * 0.1).astype(np.float32)

@@ -517,6 +517,21 @@ int sparse_fir_launch(const vnd_signal* x, const vnd_signal* y, const vnd_tap_pr
     if (rc != VND_EUNSUPPORTED) return rc;
   }
   if (!f64 && mode == MODE_SEG && p.halo > 4096 && p.frames >= 4LL * p.halo) {  // long filters on long signals
+    {  // the interior of every channel through the ring-buffer kernel (vnd_fir_ring.cu), the tail through the tile kernels below
+      long long done = 0;
+      const int rc = fir_ring_launch(p, max_prog_words, st, &done);
+      if (rc != VND_OK && rc != VND_EUNSUPPORTED) return rc;
+      if (rc == VND_OK && done > 0) {
+        p.x = reinterpret_cast<const float*>(p.x) + done;
+        p.y += done;
+        p.frames -= done;
+        if (p.frames == 0) return VND_OK;
+        if (p.halo > p.frames) p.halo = (int)((p.frames + 3) & ~3LL);
+        p.bulk_ok = (p.bulk_ok && (reinterpret_cast<uintptr_t>(p.x) % 16) == 0) ? 1 : 0;
+      }
+    }
+  }
+  if (!f64 && mode == MODE_SEG && p.halo > 4096 && p.frames >= 4LL * p.halo) {
     const int r = long_filter_r();
     const int tile = plan_long_tile(p.halo, max_prog_words, r, &smem);
     if (tile > 0) {

@@ -33,4 +33,9 @@ int fir_window_launch(const FirParams& p, int max_prog_words, cudaStream_t st);
 // tail.  Returns VND_EUNSUPPORTED (no error text) when the request does not qualify.
 int fir_tmem_launch(const FirParams& p, int max_prog_words, cudaStream_t st, long long* frames_done);
 
+// vnd_fir_ring.cu: the ring-buffer variant for long filters on planar float32 SEGMENTED programs (persistent CTAs,
+// every sample fetched once under the taps of the previous step).  Covers the interior of every channel and reports
+// the frames done per channel; the caller finishes the tail.  VND_EUNSUPPORTED (no error text) when it does not qualify.
+int fir_ring_launch(const FirParams& p, int max_prog_words, cudaStream_t st, long long* frames_done);
+
 }  // namespace vnd
