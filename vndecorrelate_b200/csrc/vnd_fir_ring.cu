@@ -7,7 +7,7 @@
 //
 // What is different is how the samples get there.  fir_tile_kernel stages tile + halo (16 384 + 28 452 samples, 177 KB)
 // per CTA with one bulk copy and waits for it: the load is not overlapped with anything and every sample is fetched 2.7
-// times (from L2).  Here one persistent CTA per SM walks along a channel in steps of C = 8192 outputs (16 warps x 32 lanes x 16) over a ring of
+// times (from L2).  Here one persistent CTA per SM walks along a channel in steps of C = 9984 outputs (12 warps x 32 lanes x 26) over a ring of
 // N = ceil((C + halo) / C) + 1 chunks of C samples: a step needs chunks s .. s + K (K = N - 2), the chunk behind them is in
 // flight while the step computes, and the chunk a step has left behind is the next one to be overwritten.  Every sample
 // is fetched once, by a producer warp (one elected lane, cp.async.bulk + mbarrier), under the taps of the previous step.
@@ -25,13 +25,16 @@ namespace vnd {
 namespace {
 
 #ifndef VND_RING_R
-#define VND_RING_R 16
+#define VND_RING_R 26
 #endif
+// Shapes measured on BASELINE config 4 (128 channels x 57.6 M frames, Gsamples/s; fir_tile_kernel: 27.5): warps x outputs per
+// lane 16 x 16: 28.0, 16 x 18: 28.2, 16 x 20: 28.3, 12 x 22: 28.3, 12 x 24: 28.6, 12 x 26: 28.7, 12 x 28: 28.6, 8 x 32: 26.6,
+// 14 x 20: 26.1 and 10 x 28: 26.8 (warps not a multiple of the four schedulers), 20 x 16 with a producer warp: 24.9.
 constexpr int kRingR = VND_RING_R;                // outputs per lane and step
 #ifndef VND_RING_WARPS
-#define VND_RING_WARPS 16
+#define VND_RING_WARPS 12
 #endif
-constexpr int kRingWarps = VND_RING_WARPS;        // compute warps (16: C = 8192, six ring slots = 192 KB for config 4's halo; 20 warps measured slower)
+constexpr int kRingWarps = VND_RING_WARPS;        // compute warps (a multiple of four: one share per scheduler)
 constexpr int kRingC = kRingWarps * 32 * kRingR;  // outputs per step = samples per chunk
 constexpr int kRingNT = kRingWarps * 32;          // no producer warp: thread 0 feeds the ring between its own taps
 
