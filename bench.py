@@ -707,9 +707,9 @@ def run_cfg4(env: Env, args, lib, N, R, VelvetNoise, C):
                     f"{Cg} channels x {L} frames per GPU (channel-sharded, planar)",
         "scaling": "weak", "value": value, "unit": UNIT, "ms": total_ms / steps, "steps": steps, "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "kernel": "fir_ring_kernel (persistent CTA per SM, ring of five 9984-sample chunks = 200 KB of shared memory, every sample "
-                               "fetched once under the taps of the previous step, 12 warps x 26 outputs per lane, two decay segments "
-                               "interleaved per warp, packed FADD2); the last three chunks of every channel through fir_tile_kernel"},
+                     "kernel": "fir_ring_kernel (persistent CTA per SM, ring of six 9216-sample chunks = 221 KB of shared memory, every sample "
+                               "fetched once under the taps of the previous step, 12 warps x 24 outputs per lane, two decay segments "
+                               "interleaved per warp, packed FADD2); the last four chunks of every channel through fir_tile_kernel"},
         "lsu_pipe": {"achieved": lsu_bytes / (kernel_ms * 1e-3) / 1e9, "peak": lsu_peak, "unit": "GB/s", "frac": lsu_bytes / (kernel_ms * 1e-3) / 1e9 / lsu_peak,
                      "note": "the binding bound: 300 taps x 4 B per output through the 128 B/clk/SM shared-memory pipe = 31 Gsamples/s per GPU at 1965 MHz"},
         "parity": parity,

@@ -586,9 +586,9 @@ def test_cfg4_long_filter_large_halo(api):
     [
         (96000, 0.3, 300, (0.85, 0.55, 0.35, 0.2), 700003, (0, 1, 2)),      # BASELINE config 4's filter, several runs per channel, channel 3 copied
         (96000, 0.2, 120, (1.0,), 400000, (0, 1, 2, 3)),                    # identity envelope (no gain multiply), four ring slots less one
-        (48000, 0.25, 64, (0.9, -0.5, 0.25), 9984 * 30, (0, 1)),             # frames a whole number of steps (9984 outputs): the tail is whole chunks
-        (96000, 0.3, 300, (0.85, 0.55, 0.35, 0.2), 9984 * 11 + 5, (0, 1, 2, 3)),   # the shortest slab the ring kernel takes (eight steps + three chunks of halo)
-        (96000, 0.3, 300, (0.85, 0.55, 0.35, 0.2), 9984 * 11 - 1, (0, 1, 2, 3)),   # one frame short of it: tile kernels only
+        (48000, 0.25, 64, (0.9, -0.5, 0.25), 9216 * 30, (0, 1)),             # frames a whole number of steps (9216 outputs): the tail is whole chunks
+        (96000, 0.3, 300, (0.85, 0.55, 0.35, 0.2), 9216 * 12 + 5, (0, 1, 2, 3)),   # the shortest slab the ring kernel takes (eight steps + four chunks of halo)
+        (96000, 0.3, 300, (0.85, 0.55, 0.35, 0.2), 9216 * 12 - 1, (0, 1, 2, 3)),   # one frame short of it: tile kernels only
     ],
 )
 def test_ring_kernel_long_filters(api, fs, duration, n_imp, envelope, frames, filtered):

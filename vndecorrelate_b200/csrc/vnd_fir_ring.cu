@@ -7,7 +7,7 @@
 //
 // What is different is how the samples get there.  fir_tile_kernel stages tile + halo (16 384 + 28 452 samples, 177 KB)
 // per CTA with one bulk copy and waits for it: the load is not overlapped with anything and every sample is fetched 2.7
-// times (from L2).  Here one persistent CTA per SM walks along a channel in steps of C = 9984 outputs (12 warps x 32 lanes x 26) over a ring of
+// times (from L2).  Here one persistent CTA per SM walks along a channel in steps of C = 9216 outputs (12 warps x 32 lanes x 24) over a ring of
 // N = ceil((C + halo) / C) + 1 chunks of C samples: a step needs chunks s .. s + K (K = N - 2), the chunk behind them is in
 // flight while the step computes, and the chunk a step has left behind is the next one to be overwritten.  Every sample
 // is fetched once, by a producer warp (one elected lane, cp.async.bulk + mbarrier), under the taps of the previous step.
@@ -25,7 +25,7 @@ namespace vnd {
 namespace {
 
 #ifndef VND_RING_R
-#define VND_RING_R 26
+#define VND_RING_R 24
 #endif
 // Shapes measured on BASELINE config 4 (128 channels x 57.6 M frames, Gsamples/s; fir_tile_kernel: 27.5): warps x outputs per
 // lane 16 x 16: 28.0, 16 x 18: 28.2, 16 x 20: 28.3, 12 x 22: 28.3, 12 x 24: 28.6, 12 x 26: 28.7, 12 x 28: 28.6, 8 x 32: 26.6,
@@ -151,7 +151,16 @@ __global__ void __launch_bounds__(kRingNT, 1) fir_ring_kernel(const RingParams P
       const int* seg = sprog + 1;
       for (int s = 0; s < ns; ++s) {
         pump();
-        for (int j = (s == 0 ? 0 : s + K); j <= s + K; ++j) mbar_wait(&full[j % N], (unsigned)((j / N) & 1));
+        for (int j = (s == 0 ? 0 : s + K); j <= s + K; ++j) {
+          // Thread 0 is the only producer: while it waits for a chunk it keeps feeding the ring (the chunk it waits for may
+          // not even be requested yet, if another warp was still reading the slot when thread 0 last looked); the other
+          // lanes spin.  Waiting with a plain spin in thread 0 deadlocks as soon as a warp lags by more than a step.
+          if (tid == 0) {
+            while (!ring_try(&full[j % N], (unsigned)((j / N) & 1))) pump();
+          } else {
+            mbar_wait(&full[j % N], (unsigned)((j / N) & 1));
+          }
+        }
         const int pos0 = (s % N) * kRingC + 32 * kRingR * warp;  // ring offset of this warp's first output sample
         float yv[kRingR];
 #pragma unroll
