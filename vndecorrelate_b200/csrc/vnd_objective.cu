@@ -71,6 +71,26 @@ __device__ __forceinline__ void run_candidate(const float* __restrict__ px, cons
 // copy in which its operands are 16-byte aligned: one LDS.128 per group and tap instead of four LDS.32
 // (same shared-memory wavefronts, a quarter of the load instructions).  `dec` holds the program's taps
 // decoded once per candidate as word offsets (offset & 3) * span4 + (offset & ~3) into the copies.
+#ifndef VND_OBJ_DUAL
+#define VND_OBJ_DUAL 0  // 1: two decay segments interleaved per warp (needs 128 registers: VND_OBJ_NT <= 512).  Measured on 16 clips x 1024
+                        // strengths x 30 s: 129 k evaluations/s with 16 warps against 156 k for the single stream with 20 warps (147 k
+                        // with 16): unlike in fir_ring_kernel, the warps the second stream costs are worth more to the polar moments.
+#endif
+template <int R, bool SUB>
+__device__ __forceinline__ void obj_tap_v4(const float* __restrict__ px, int off, float (&acc)[R]) {
+  const float4* q = reinterpret_cast<const float4*>(px + off);
+#pragma unroll
+  for (int j = 0; j < R / 4; ++j) {
+    const float4 v = q[32 * j];
+    if constexpr (SUB) {
+      obj_sub2(acc[4 * j], acc[4 * j + 1], v.x, v.y);
+      obj_sub2(acc[4 * j + 2], acc[4 * j + 3], v.z, v.w);
+    } else {
+      obj_add2(acc[4 * j], acc[4 * j + 1], v.x, v.y);
+      obj_add2(acc[4 * j + 2], acc[4 * j + 3], v.z, v.w);
+    }
+  }
+}
 template <int R>
 __device__ __forceinline__ void run_candidate_v4(const float* __restrict__ px, const int* __restrict__ prog, const int* __restrict__ dec,
                                                  int apply_gain, float (&yv)[R]) {
@@ -79,30 +99,106 @@ __device__ __forceinline__ void run_candidate_v4(const float* __restrict__ px, c
   const int S = prog[0];
   const int* seg = prog + 1;
   const int* tp = dec;
+#if VND_OBJ_DUAL
+  // Two decay segments at a time (their sums are independent, optimization.py's candidates go through decorrelation.py:402-414):
+  // the loads of both taps are issued before either's adds, which doubles the loads a warp has in flight; the running output
+  // still adds the scaled sums in segment order.  Offsets are read one tap ahead (a word of slack follows the decoded list).
+  for (int s = 0; s < S; s += 2) {
+    const bool two = s + 1 < S;
+    const int na_neg = seg[3 * s], na = na_neg + seg[3 * s + 1];
+    const int nb_neg = two ? seg[3 * s + 3] : 0, nb = two ? nb_neg + seg[3 * s + 4] : 0;
+    const int* ta = tp;
+    const int* tb = tp + na;
+    tp += na + nb;
+    float accA[R], accB[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      accA[r] = 0.0f;
+      accB[r] = 0.0f;
+    }
+    const int nboth = na < nb ? na : nb;
+    int oa = ta[0], ob = tb[0];
+    int k = 0;
+    for (; k < nboth; ++k) {
+      const float4* qa = reinterpret_cast<const float4*>(px + oa);
+      const float4* qb = reinterpret_cast<const float4*>(px + ob);
+      oa = ta[k + 1];
+      ob = tb[k + 1];
+      float4 va[R / 4], vb[R / 4];
+#pragma unroll
+      for (int j = 0; j < R / 4; ++j) va[j] = qa[32 * j];
+#pragma unroll
+      for (int j = 0; j < R / 4; ++j) vb[j] = qb[32 * j];
+      if (k < na_neg) {
+#pragma unroll
+        for (int j = 0; j < R / 4; ++j) {
+          obj_sub2(accA[4 * j], accA[4 * j + 1], va[j].x, va[j].y);
+          obj_sub2(accA[4 * j + 2], accA[4 * j + 3], va[j].z, va[j].w);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < R / 4; ++j) {
+          obj_add2(accA[4 * j], accA[4 * j + 1], va[j].x, va[j].y);
+          obj_add2(accA[4 * j + 2], accA[4 * j + 3], va[j].z, va[j].w);
+        }
+      }
+      if (k < nb_neg) {
+#pragma unroll
+        for (int j = 0; j < R / 4; ++j) {
+          obj_sub2(accB[4 * j], accB[4 * j + 1], vb[j].x, vb[j].y);
+          obj_sub2(accB[4 * j + 2], accB[4 * j + 3], vb[j].z, vb[j].w);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < R / 4; ++j) {
+          obj_add2(accB[4 * j], accB[4 * j + 1], vb[j].x, vb[j].y);
+          obj_add2(accB[4 * j + 2], accB[4 * j + 3], vb[j].z, vb[j].w);
+        }
+      }
+    }
+    for (int ka = k; ka < na; ++ka) {
+      if (ka < na_neg) obj_tap_v4<R, true>(px, ta[ka], accA);
+      else obj_tap_v4<R, false>(px, ta[ka], accA);
+    }
+    for (int kb = k; kb < nb; ++kb) {
+      if (kb < nb_neg) obj_tap_v4<R, true>(px, tb[kb], accB);
+      else obj_tap_v4<R, false>(px, tb[kb], accB);
+    }
+    if (apply_gain) {
+      const float ga = __int_as_float(seg[3 * s + 2]);
+#pragma unroll
+      for (int r = 0; r < R; r += 2) obj_mul2(accA[r], accA[r + 1], ga, ga);
+    }
+#pragma unroll
+    for (int r = 0; r < R; r += 2) obj_add2(yv[r], yv[r + 1], accA[r], accA[r + 1]);
+    if (two) {
+      if (apply_gain) {
+        const float gb = __int_as_float(seg[3 * s + 5]);
+#pragma unroll
+        for (int r = 0; r < R; r += 2) obj_mul2(accB[r], accB[r + 1], gb, gb);
+      }
+#pragma unroll
+      for (int r = 0; r < R; r += 2) obj_add2(yv[r], yv[r + 1], accB[r], accB[r + 1]);
+    }
+  }
+#else
   for (int s = 0; s < S; ++s) {
     const int n_neg = seg[3 * s], n_pos = seg[3 * s + 1];
     const float gain = __int_as_float(seg[3 * s + 2]);
     float acc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.0f;
+    int nxt = tp[0];  // offsets are read one tap ahead (a word of slack follows the decoded list)
     for (int k = 0; k < n_neg; ++k) {
-      const float4* q = reinterpret_cast<const float4*>(px + tp[k]);
-#pragma unroll
-      for (int j = 0; j < R / 4; ++j) {
-        const float4 v = q[32 * j];
-        obj_sub2(acc[4 * j], acc[4 * j + 1], v.x, v.y);
-        obj_sub2(acc[4 * j + 2], acc[4 * j + 3], v.z, v.w);
-      }
+      const int off = nxt;
+      nxt = tp[k + 1];
+      obj_tap_v4<R, true>(px, off, acc);
     }
     tp += n_neg;
     for (int k = 0; k < n_pos; ++k) {
-      const float4* q = reinterpret_cast<const float4*>(px + tp[k]);
-#pragma unroll
-      for (int j = 0; j < R / 4; ++j) {
-        const float4 v = q[32 * j];
-        obj_add2(acc[4 * j], acc[4 * j + 1], v.x, v.y);
-        obj_add2(acc[4 * j + 2], acc[4 * j + 3], v.z, v.w);
-      }
+      const int off = nxt;
+      nxt = tp[k + 1];
+      obj_tap_v4<R, false>(px, off, acc);
     }
     tp += n_pos;
     if (apply_gain) {
@@ -112,6 +208,7 @@ __device__ __forceinline__ void run_candidate_v4(const float* __restrict__ px, c
 #pragma unroll
     for (int r = 0; r < R; r += 2) obj_add2(yv[r], yv[r + 1], acc[r], acc[r + 1]);
   }
+#endif
 }
 
 // Shared memory: float x0[4][span4] (copy c = channel 0 shifted by c samples) | float x1[TILE] |
